@@ -1,0 +1,161 @@
+/*
+ * metro.h -- C-ABI of libmetro.so: the B200-native drop-in for the MeTRo inference hot path
+ *            (RGB crops -> ResNet-v2-50/101 -> J x D volumetric heatmaps -> soft-argmax -> mm).
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference
+ * repository isarandi/metro-pose3d).  The reference exposes this path as a TensorFlow frozen
+ * graph: feed 'input:0', fetch 'output' / 'joint_edges' / 'joint_names' (inference.py:31-43,
+ * src/main.py:106-161).  A C-ABI replacement therefore has: create (== import_graph_def + weight
+ * constants), infer (== sess.run(poses_tensor)), joint tables (== the two Const nodes), destroy.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (streams travel as void*).
+ *   - every function returns a metro_status; the message for the last failure on the calling
+ *     thread is available from metro_last_error().  Nothing throws or exits across the ABI.
+ *   - METRO_ERR_VALUE marks the conditions for which the reference raises ValueError
+ *     (src/model/resnet_v2.py:213-214, src/model/resnet_utils.py:333,345,348).
+ *   - device buffers are owned by the caller; the handle owns weights + a workspace arena sized at
+ *     create time for `max_batch`.  No allocation, no synchronisation inside metro_infer.
+ *   - a handle is bound to one device and is not thread-safe (the reference runs one tf.Session
+ *     on the caller's thread, src/helpers.py:123-127).
+ */
+#ifndef METRO_H_
+#define METRO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum metro_status {
+  METRO_OK = 0,
+  METRO_ERR_VALUE = 1,       /* invalid argument: the reference raises ValueError here          */
+  METRO_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed                              */
+  METRO_ERR_NO_DEVICE = 3,   /* no sm_100 device: the product path refuses to run (no fallback)  */
+  METRO_ERR_NOMEM = 4,
+  METRO_ERR_INTERNAL = 5
+} metro_status;
+
+/* Element type of the head tensor (output of the 1x1 'logits' conv, input of the soft-argmax).
+ * The reference computes the logits in FLAGS.dtype (float16 by default, src/options.py:73) and
+ * casts to float32 (src/model/architectures.py:34). */
+typedef enum metro_dtype { METRO_F32 = 0, METRO_F16 = 1 } metro_dtype;
+
+/* Static description of one exported model; the fields are the reference's FLAGS that shape the
+ * frozen graph (src/options.py:41,96,113,118,119; src/main.py:119-127). */
+typedef struct metro_spec {
+  int32_t arch;               /* 50 | 101           FLAGS.architecture resnet_v2_50 / resnet_v2_101 */
+  int32_t stride;             /* 4|8|16|32          FLAGS.stride_test                               */
+  int32_t n_joints_model;     /* joints predicted by the head; the root is the LAST one            */
+  int32_t depth;              /* 8                  FLAGS.depth                                     */
+  int32_t centered_stride;    /* 1                  FLAGS.centered_stride                           */
+  int32_t proc_side;          /* 256                FLAGS.proc_side                                 */
+  float box_size_mm;          /* 2200               FLAGS.box_size_mm                               */
+  int32_t n_joints_out;       /* length of `permutation`                                            */
+  const int32_t *permutation; /* output joint j = model joint permutation[j]  (main.py:119-127)     */
+  int32_t max_batch;          /* arena is sized for this many crops per metro_infer call            */
+  int32_t head_dtype;         /* metro_dtype of the head tensor kept in HBM                         */
+  int32_t keep_activations;   /* debug: give every layer its own buffer (metro_debug_read)          */
+} metro_spec;
+
+typedef struct metro_handle metro_handle;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char *metro_last_error(void);
+const char *metro_version(void);
+
+/* ---- plan (host only, usable without a GPU) ---------------------------------------------------- */
+/* Number of float32 values the weight blob must hold for `spec`
+ * (== all variables under MainPart/resnet_v2_*, src/model/architectures.py:24). */
+metro_status metro_blob_floats(const metro_spec *spec, uint64_t *n_floats);
+/* Writes a JSON description of the layer plan (the replay of resnet_utils.py:307-350) into `buf`;
+ * `*needed` receives the byte count including the terminator. */
+metro_status metro_plan_describe(const metro_spec *spec, char *buf, size_t buf_bytes, size_t *needed);
+
+/* ---- model: replaces estimate_pose()'s graph import (inference.py:31-38) ----------------------- */
+/* `weights_blob`: host float32 array in the order documented in metro_pose3d_b200/weights.py
+ * (TF variable order, conv filters HWIO, BatchNorm as gamma/beta/moving_mean/moving_variance). */
+metro_status metro_create(const metro_spec *spec, const float *weights_blob, uint64_t n_floats,
+                          int32_t device, metro_handle **out);
+metro_status metro_destroy(metro_handle *h);
+metro_status metro_workspace_bytes(const metro_handle *h, uint64_t *bytes);
+
+/* ---- inference: replaces sess.run(poses_tensor) (inference.py:25-27) --------------------------- */
+/* images_dev: device float32 NHWC [n,256,256,3] in [0,1] ('input:0', main.py:109-110)
+ * poses_dev : device float32 [n, n_joints_out, 3], root-relative millimetres ('output', main.py:127)
+ * stream    : cudaStream_t as void* (NULL = default stream).  Asynchronous. */
+metro_status metro_infer(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev,
+                         void *stream);
+/* Same through HOST buffers: pinned or pageable host memory in, host memory out; copies and a
+ * final stream synchronisation happen inside the call (this is what sess.run does for numpy
+ * feeds, inference.py:26-27). */
+metro_status metro_infer_host(metro_handle *h, const float *images_host, int32_t n,
+                              float *poses_host);
+/* uint8 RGB crops (the /255 of src/improc.py:56-61 is fused into the first
+ * kernel).  images_u8_dev: device uint8 NHWC [n,256,256,3]. */
+metro_status metro_infer_u8(metro_handle *h, const uint8_t *images_u8_dev, int32_t n,
+                            float *poses_dev, void *stream);
+
+/* ---- stand-alone soft-argmax: replaces net_output_to_heatmap_and_coords + heatmap_to_metric +
+ *      root_relative + gather (volumetric.py:227-235,288-306; tfu.py:466-499; tfu3d.py:23-25;
+ *      main.py:127) ------------------------------------------------------------------------------ */
+typedef struct metro_softargmax_desc {
+  int32_t side;               /* heatmap height == width (256 / stride)                            */
+  int32_t n_joints_model;
+  int32_t depth;
+  int32_t stride;
+  int32_t centered_stride;
+  int32_t proc_side;
+  float box_size_mm;
+  int32_t n_joints_out;
+  const int32_t *permutation;
+  int32_t head_dtype;         /* metro_dtype                                                       */
+  int32_t splits;             /* 0 = choose; >0 = CTAs per crop (tuning / tests)                   */
+  int32_t lanes;              /* 0 = choose; >0 = pixel lanes per CTA (tuning / tests)             */
+} metro_softargmax_desc;
+
+metro_status metro_softargmax_workspace_bytes(const metro_softargmax_desc *d, int32_t n,
+                                              uint64_t *bytes);
+/* head_dev: device NHWC [n, side, side, depth*n_joints_model], channel c = d*J + j
+ * (volumetric.py:231-232).  workspace_dev must be zero-filled once after allocation; the kernel
+ * leaves it zeroed. */
+metro_status metro_softargmax(const metro_softargmax_desc *d, const void *head_dev, int32_t n,
+                              float *poses_dev, void *workspace_dev, void *stream);
+
+/* ---- single fused convolution (operator-level entry point used by the parity tests) ----------- */
+typedef struct metro_conv_desc {
+  int32_t n, in_side, cin, cout, k, stride, rate, pad_lo;  /* conv2d_same geometry (resnet_utils.py:82-135) */
+  int32_t relu;                 /* apply ReLU to output 1                                           */
+  int32_t out_dtype;            /* metro_dtype of output 1                                          */
+  int32_t res_stride, res_shift;/* residual = res[:, s::stride, s::stride, :] (resnet_v2.py:120-121); 0 = none */
+  int32_t cin2;                 /* >0: second 1x1 source fused into the same accumulator (shortcut) */
+} metro_conv_desc;
+/* x: fp16 NHWC [n,in,in,cin]; w: host float32 HWIO [k,k,cin,cout]; x2/w2: optional second source
+ * (fp16 NHWC [n,out,out,cin2], host float32 [1,1,cin2,cout]); scale/shift: host float32 [cout]
+ * (folded BN or 1/bias); res: optional fp16 NHWC; y: output 1; scale2/shift2 + y2: optional second
+ * output y2 = relu(scale2 * fp16(y) + shift2) as fp16 (the next unit's pre-activation,
+ * resnet_v2.py:119). */
+metro_status metro_conv2d(const metro_conv_desc *d, const void *x_dev, const float *w_host,
+                          const void *x2_dev, const float *w2_host, const float *scale_host,
+                          const float *shift_host, const void *res_dev, void *y_dev,
+                          const float *scale2_host, const float *shift2_host, void *y2_dev,
+                          int32_t device, void *stream);
+
+/* ---- debug ------------------------------------------------------------------------------------- */
+/* With spec.keep_activations: copy the named activation of the last metro_infer call to host.
+ * Names: "conv1", "pool1", "<unit>/conv1", "<unit>/conv2", "<unit>/out", "<unit>/pre", "head".
+ * `*elems` receives the element count; dtype is fp16 except "head" (spec.head_dtype). */
+metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf, uint64_t buf_bytes,
+                              uint64_t *elems);
+/* Per-launch device times (ms) of the last metro_profile call, one entry per kernel launch. */
+metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev,
+                           float *ms_out, char *names_buf, size_t names_bytes, int32_t *n_launches);
+/* Number of kernel launches one metro_infer(n) enqueues. */
+metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METRO_H_ */

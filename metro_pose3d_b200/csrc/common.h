@@ -1,0 +1,42 @@
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/metro.h"
+
+namespace metro {
+
+void set_error(const char *fmt, ...);
+metro_status fail(metro_status st, const char *fmt, ...);
+
+#define METRO_CUDA(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return ::metro::fail(METRO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                           __FILE__, __LINE__);                                                       \
+  } while (0)
+
+constexpr int kMaxJointsOut = 64;
+
+// ---- soft-argmax ------------------------------------------------------------------------------------
+struct SoftargmaxLaunch {
+  const void *head;
+  float *out;
+  double *partials;        // [n][splits][J][5] : M, S, Sx, Sy, Sz
+  unsigned int *counters;  // [n], zero between launches
+  int n, H, W, J, D, C;
+  int n_out, root;
+  int perm[kMaxJointsOut];
+  double mul_x, mul_y, mul_z;  // mm per unit of (Sx/S), (Sy/S), (Sz/S)
+  int splits, lanes, slots, ppc;
+  int head_f16;
+};
+metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLaunch &L);
+size_t softargmax_workspace_bytes(const SoftargmaxLaunch &L);
+metro_status softargmax_launch(const SoftargmaxLaunch &L, cudaStream_t stream);
+
+}  // namespace metro

@@ -1,0 +1,392 @@
+// Fused implicit-GEMM convolution for sm_100a.
+//
+//   D[M = N*Ho*Wo pixels, Cout] = sum over taps (kh,kw) and 64-channel blocks of
+//                                 X[n, ho*s + kh*r - pad, wo*s + kw*r - pad, c] * W[kh,kw,c,cout]
+//
+// One kernel serves every convolution of the ResNet body (resnet_v2.py:123-136,234-236):
+//   * A operand: NHWC fp16 activations fetched by TMA as 4-D boxes [64 ch, Wo, th, nb] (128 output
+//     pixels = th full output rows of nb crops) at the tap's shifted coordinate; TMA's out-of-bounds
+//     zero fill IS the convolution's zero padding (resnet_utils.py:120-135), dilation is a larger
+//     shift, and a stride-2 conv reads four (row,col)-parity views of the input (tensor maps with
+//     doubled strides), so no im2col buffer and no strided gather exists anywhere.
+//   * B operand: weights pre-packed [Cout][K] fp16 K-major, 2-D TMA boxes [64, BLOCK_N].
+//   * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
+//   * accumulators live in TMEM (fp32), double-buffered so the epilogue of tile i overlaps the
+//     main loop of tile i+1; the kernel is persistent (one CTA per SM, static round-robin tiles).
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator,
+//     4..7 = epilogue (thread = accumulator row = output pixel).
+//   * epilogue fuses folded BN / bias, the residual add (identity shortcut, optionally sub-sampled
+//     with the centred-stride offset, resnet_v2.py:120-121), ReLU, and the *next* layer's
+//     pre-activation BN+ReLU as a second output (resnet_v2.py:119), so no stand-alone
+//     normalisation pass ever touches HBM.  The projection shortcut (resnet_v2.py:123-125) is a
+//     second A source accumulated into the same TMEM tile (K concatenation).
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "conv_gemm.h"
+#include "ptx.cuh"
+
+namespace metro {
+
+namespace {
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kStages = BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 6 : (BLOCK_N <= 160 ? 5 : 4));
+  static constexpr int kABytes = kTileM * kTileK * 2;          // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kTileK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAccCols = BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256);  // per stage
+  static constexpr int kTmemCols = 2 * kAccCols;               // power of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * BLOCK_N * 4 + 256 + 1024;
+};
+
+constexpr int kThreads = 256;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment: required by the 128B swizzle atoms (8 rows x 128 B)
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                          ~uintptr_t(1023));
+  unsigned char *tiles = smem;
+  float *s_par = reinterpret_cast<float *>(smem + C::kStages * C::kStageBytes);   // [4][BLOCK_N]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_par + 4 * BLOCK_N);
+  uint64_t *full = bars, *empty = bars + C::kStages;
+  uint64_t *tfull = bars + 2 * C::kStages, *tempty = tfull + 2;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kb = p.taps * p.cblk0 + p.cblk1;
+  const int n_tiles_total = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.amap[0]);
+    ptx::prefetch_tensormap(&p.bmap);
+    if (p.cblk1) ptx::prefetch_tensormap(&p.a2map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(s_tmem, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        int n0, h0;
+        if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
+        else { n0 = mt * p.nb; h0 = 0; }
+        for (int kb = 0; kb < n_kb; ++kb) {
+          ptx::mbar_wait(empty + stage, phase ^ 1);
+          unsigned char *sa = tiles + stage * C::kStageBytes;
+          unsigned char *sb = sa + C::kABytes;
+          ptx::mbar_arrive_expect_tx(full + stage, C::kStageBytes);
+          const int k0 = p.taps * p.cblk0;
+          if (kb < k0) {
+            const int tap = kb / p.cblk0, cb = kb - tap * p.cblk0;
+            ptx::tma_load_4d(sa, &p.amap[p.tap_map[tap]], full + stage, cb * kTileK, p.tap_dw[tap],
+                             h0 + p.tap_dh[tap], n0);
+          } else {
+            ptx::tma_load_4d(sa, &p.a2map, full + stage, (kb - k0) * kTileK, 0, h0, n0);
+          }
+          ptx::tma_load_2d(sb, &p.bmap, full + stage, kb * kTileK, nt * BLOCK_N);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BLOCK_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        ptx::mbar_wait(tempty + acc, aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          ptx::mbar_wait(full + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(tiles + stage * C::kStageBytes);
+          const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
+          const uint64_t db = ptx::make_sw128_kmajor_desc(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < kTileK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(empty + stage);           // frees the smem slot when these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(tfull + acc);               // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int q = warp - 4;                          // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 128;                // 0..127 == accumulator row
+    int acc = 0;
+    uint32_t aphase = 0;
+    const int hw = p.ho * p.wo;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      // stage the per-channel epilogue vectors of this N tile
+      ptx::named_bar_sync(1, 128);
+      for (int i = et; i < BLOCK_N; i += 128) {
+        const int c = nt * BLOCK_N + i;
+        s_par[i] = p.scale[c];
+        s_par[BLOCK_N + i] = p.shift[c];
+        if (p.out2) { s_par[2 * BLOCK_N + i] = p.scale2[c]; s_par[3 * BLOCK_N + i] = p.shift2[c]; }
+      }
+      ptx::named_bar_sync(1, 128);
+
+      const int m = mt * kTileM + et;
+      const bool valid = m < p.m_total;
+      const __half *res_row = nullptr;
+      if (p.res && valid) {
+        const int n = m / hw, rem = m - n * hw;
+        const int oh = rem / p.wo, ow = rem - oh * p.wo;
+        res_row = p.res + (size_t(n * p.res_h + oh * p.res_stride + p.res_shift) * p.res_w +
+                           ow * p.res_stride + p.res_shift) * p.cout;
+      }
+      ptx::mbar_wait(tfull + acc, aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * C::kAccCols;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        const int col0 = nt * BLOCK_N + chunk * 32;
+        if (col0 >= p.cout) break;                   // uniform: padded head columns
+        uint32_t v[32];
+        __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
+        ptx::tmem_ld_32x32(taddr + chunk * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = col0 + 8 * g;
+          if (col >= p.cout) break;                  // uniform (cout is a multiple of 8)
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int pi = chunk * 32 + 8 * g + i;
+            f[i] = fmaf(__uint_as_float(v[8 * g + i]), s_par[pi], s_par[BLOCK_N + pi]);
+          }
+          if (valid) {
+            if (res_row) {
+              const uint4 r = *reinterpret_cast<const uint4 *>(res_row + col);
+              const __half2 *rh = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 rf = __half22float2(rh[i]);
+                f[2 * i] += rf.x;
+                f[2 * i + 1] += rf.y;
+              }
+            }
+            if (p.relu1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            const size_t off = size_t(m) * p.cout + col;
+            if (p.out1_f32) {
+              if (p.out1) {
+                float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out1) + off);
+                dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+              }
+            } else {
+              uint4 o;
+              __half2 *oh2 = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) oh2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+              if (p.out1) *reinterpret_cast<uint4 *>(static_cast<__half *>(p.out1) + off) = o;
+              if (p.out2) {
+                uint4 o2;
+                __half2 *o2h = reinterpret_cast<__half2 *>(&o2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int pi = chunk * 32 + 8 * g + 2 * i;
+                  const float2 y = __half22float2(oh2[i]);     // the fp16 value the consumer would read
+                  const float a = fmaxf(fmaf(y.x, s_par[2 * BLOCK_N + pi], s_par[3 * BLOCK_N + pi]), 0.f);
+                  const float b = fmaxf(fmaf(y.y, s_par[2 * BLOCK_N + pi + 1], s_par[3 * BLOCK_N + pi + 1]), 0.f);
+                  o2h[i] = __floats2half2_rn(a, b);
+                }
+                *reinterpret_cast<uint4 *>(p.out2 + off) = o2;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty + acc);
+      if (++acc == 2) { acc = 0; aphase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---- driver entry point -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int BLOCK_N>
+metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = L.prm.m_tiles * L.prm.n_tiles;
+  if (tiles == 0) return METRO_OK;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  conv_gemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, stream>>>(L.prm);
+  METRO_CUDA(cudaGetLastError());
+  return METRO_OK;
+}
+
+}  // namespace
+
+metro_status make_act_tensor_map(CUtensorMap *map, const void *base, int n, int h, int w, int c, int sub, int ph,
+                                 int pw, int box_w, int box_h, int box_n) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  // view [C, W/sub, H/sub, N] of the NHWC tensor, starting at pixel (ph, pw)
+  const cuuint64_t dims[4] = {cuuint64_t(c), cuuint64_t(w / sub), cuuint64_t(h / sub), cuuint64_t(n)};
+  const cuuint64_t strides[3] = {cuuint64_t(sub) * c * 2, cuuint64_t(sub) * w * c * 2, cuuint64_t(h) * w * c * 2};
+  const cuuint32_t box[4] = {cuuint32_t(kTileK), cuuint32_t(box_w), cuuint32_t(box_h), cuuint32_t(box_n)};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  void *addr = const_cast<unsigned char *>(static_cast<const unsigned char *>(base)) + (size_t(ph) * w + pw) * c * 2;
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, addr, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d sub=%d box=%d,%d,%d) -> %d", n,
+                h, w, c, sub, box_w, box_h, box_n, int(r));
+  return METRO_OK;
+}
+
+metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout_pad, int k_total, int block_n) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {cuuint64_t(k_total), cuuint64_t(cout_pad)};
+  const cuuint64_t strides[1] = {cuuint64_t(k_total) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(kTileK), cuuint32_t(block_n)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled(weights cout_pad=%d k=%d block_n=%d) -> %d", cout_pad, k_total,
+                block_n, int(r));
+  return METRO_OK;
+}
+
+int conv_gemm_pick_block_n(int cout) {
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  if (cout <= 160) return 160;
+  return 256;
+}
+
+int conv_gemm_cout_pad(int cout, int block_n) { return (cout + block_n - 1) / block_n * block_n; }
+
+metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side) {
+  const int wo = out_side, ho = out_side;
+  if (wo < 8 || wo > kTileM || (wo & (wo - 1)) != 0)
+    return fail(METRO_ERR_VALUE, "conv_gemm: output side %d must be a power of two in [8,128]", wo);
+  p.wo = wo; p.ho = ho;
+  int th = kTileM / wo;
+  if (th > ho) th = ho;
+  p.th = th;
+  p.nb = kTileM / (wo * th);
+  p.tiles_per_img = p.nb == 1 ? (ho / th) : 1;
+  return METRO_OK;
+}
+
+metro_status conv_gemm_set_batch(ConvGemmParams &p, int n) {
+  p.m_total = n * p.ho * p.wo;
+  p.m_tiles = (p.m_total + kTileM - 1) / kTileM;
+  return METRO_OK;
+}
+
+metro_status conv_gemm_set_taps(ConvGemmParams &p, int k, int stride, int rate, int pad_lo) {
+  if (k * k > kMaxTaps) return fail(METRO_ERR_VALUE, "conv_gemm: kernel size %d not supported", k);
+  if (stride != 1 && stride != 2) return fail(METRO_ERR_VALUE, "conv_gemm: stride %d not supported", stride);
+  p.taps = k * k;
+  for (int kh = 0; kh < k; ++kh)
+    for (int kw = 0; kw < k; ++kw) {
+      const int t = kh * k + kw;
+      const int oh = kh * rate - pad_lo, ow = kw * rate - pad_lo;   // input offset relative to out*stride
+      if (stride == 1) {
+        p.tap_map[t] = 0; p.tap_dh[t] = (signed char)oh; p.tap_dw[t] = (signed char)ow;
+      } else {
+        const int ph = ((oh % 2) + 2) % 2, pw = ((ow % 2) + 2) % 2;
+        p.tap_map[t] = (signed char)(ph * 2 + pw);
+        p.tap_dh[t] = (signed char)((oh - ph) / 2);
+        p.tap_dw[t] = (signed char)((ow - pw) / 2);
+      }
+    }
+  return METRO_OK;
+}
+
+void conv_gemm_pack_weights(const float *w, int k, int cin, int cout, const float *w2, int cin2, int cout_pad,
+                            __half *dst) {
+  const size_t K = size_t(k) * k * cin + cin2;
+  std::memset(dst, 0, size_t(cout_pad) * K * sizeof(__half));
+  for (int t = 0; t < k * k; ++t)
+    for (int c = 0; c < cin; ++c) {
+      const float *src = w + (size_t(t) * cin + c) * cout;
+      for (int o = 0; o < cout; ++o) dst[size_t(o) * K + size_t(t) * cin + c] = __float2half_rn(src[o]);
+    }
+  for (int c = 0; c < cin2; ++c) {
+    const float *src = w2 + size_t(c) * cout;
+    for (int o = 0; o < cout; ++o) dst[size_t(o) * K + size_t(k) * k * cin + c] = __float2half_rn(src[o]);
+  }
+}
+
+metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
+  switch (L.block_n) {
+    case 64: return launch_t<64>(L, num_sms, stream);
+    case 128: return launch_t<128>(L, num_sms, stream);
+    case 160: return launch_t<160>(L, num_sms, stream);
+    case 256: return launch_t<256>(L, num_sms, stream);
+    default: return fail(METRO_ERR_INTERNAL, "conv_gemm: unsupported BLOCK_N %d", L.block_n);
+  }
+}
+
+}  // namespace metro

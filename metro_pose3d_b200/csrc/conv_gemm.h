@@ -1,0 +1,63 @@
+// Fused implicit-GEMM convolution on tcgen05 tensor cores (sm_100a): host-side description.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "common.h"
+
+namespace metro {
+
+constexpr int kTileM = 128;     // output pixels per tile (UMMA M)
+constexpr int kTileK = 64;      // fp16 channels per K block = one 128-byte swizzle row
+constexpr int kMaxTaps = 9;
+
+// Kernel parameters (passed by value as a __grid_constant__; tensor maps must be 64-byte aligned).
+struct alignas(64) ConvGemmParams {
+  CUtensorMap amap[4];   // source 0, NHWC fp16, viewed as [C, W', H', N]; 4 = (row,col) parity views
+                         // of a stride-2 conv (entry 0 only for stride 1)
+  CUtensorMap a2map;     // optional source 1 (1x1 on the output grid): the projection shortcut
+  CUtensorMap bmap;      // packed weights [cout_pad][K_total] fp16, K-major
+  // K loop: taps x cblk0 blocks from source 0, then cblk1 blocks from source 1
+  int taps, cblk0, cblk1;
+  signed char tap_map[12], tap_dh[12], tap_dw[12];
+  // M tiling: a tile is 128 consecutive output pixels = th full rows of nb images
+  int m_total, wo, ho, th, nb, tiles_per_img, m_tiles, n_tiles, cout;
+  // epilogue: y = acc*scale + shift (+ res) ; relu? ; store y (fp16|fp32) ;
+  //           y2 = relu(fp16(y)*scale2 + shift2) -> fp16 (the consumer's pre-activation)
+  const float *scale, *shift, *scale2, *shift2;
+  const __half *res;
+  int res_stride, res_shift, res_h, res_w;
+  void *out1;
+  __half *out2;
+  int out1_f32, relu1;
+};
+
+struct ConvGemmLaunch {
+  ConvGemmParams prm;
+  int block_n = 128;       // 64 | 128 | 160 | 256
+  std::string name;
+  double flops_per_img = 0;
+};
+
+// Tensor-map helpers (driver entry point resolved at run time; no link-time libcuda dependency).
+metro_status make_act_tensor_map(CUtensorMap *map, const void *base, int n, int h, int w, int c,
+                                 int sub, int ph, int pw, int box_w, int box_h, int box_n);
+metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout_pad, int k_total, int block_n);
+
+int conv_gemm_pick_block_n(int cout);
+int conv_gemm_cout_pad(int cout, int block_n);
+// Fills the M-tiling fields for `n` images of an out_side x out_side output.
+metro_status conv_gemm_set_batch(ConvGemmParams &p, int n);
+metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side);
+metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream);
+// Packs HWIO float32 filters into [cout_pad][K] fp16 in the kernel's K-block order; `w2` (1x1,
+// [cin2][cout]) is appended along K.
+void conv_gemm_pack_weights(const float *w_hwio, int k, int cin, int cout, const float *w2, int cin2,
+                            int cout_pad, __half *dst);
+// Tap table for a k x k conv with the given stride / rate / leading pad.
+metro_status conv_gemm_set_taps(ConvGemmParams &p, int k, int stride, int rate, int pad_lo);
+
+}  // namespace metro

@@ -1,0 +1,603 @@
+// C-ABI of libmetro.so (include/metro.h): plan -> device weights + arena + launch list -> infer.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "conv_gemm.h"
+#include "plan.h"
+#include "root_pool.h"
+
+namespace metro {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+metro_status fail(metro_status st, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return st;
+}
+
+namespace {
+
+constexpr double kBnEps = 1e-5;   // architectures.py:10
+
+// gamma, beta, mean, var (c each) -> scale, shift (computed in double, stored float)
+void bn_affine(const float *bn, int c, std::vector<float> &scale, std::vector<float> &shift) {
+  scale.resize(c); shift.resize(c);
+  const float *g = bn, *b = bn + c, *m = bn + 2 * c, *v = bn + 3 * c;
+  for (int i = 0; i < c; ++i) {
+    const double s = double(g[i]) / std::sqrt(double(v[i]) + kBnEps);
+    scale[i] = float(s);
+    shift[i] = float(double(b[i]) - double(m[i]) * s);
+  }
+}
+
+struct DeviceArena {
+  std::vector<void *> ptrs;
+  size_t total = 0;
+  ~DeviceArena() { for (void *p : ptrs) cudaFree(p); }
+  metro_status alloc(void **out, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    void *p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(METRO_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    ptrs.push_back(p); total += bytes; *out = p;
+    return METRO_OK;
+  }
+  template <typename T>
+  metro_status upload(T **out, const std::vector<T> &host, size_t pad_to = 0) {
+    const size_t n = pad_to > host.size() ? pad_to : host.size();
+    void *p = nullptr;
+    metro_status st = alloc(&p, n * sizeof(T));
+    if (st != METRO_OK) return st;
+    METRO_CUDA(cudaMemset(p, 0, n * sizeof(T)));
+    METRO_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<T *>(p);
+    return METRO_OK;
+  }
+};
+
+struct GemmSpec {
+  std::string name;
+  int n_max = 0;
+  const __half *src = nullptr; int in_side = 0, cin = 0;
+  int k = 1, stride = 1, rate = 1, pad_lo = 0, out_side = 0, cout = 0;
+  const float *w = nullptr;                 // host HWIO
+  const __half *src2 = nullptr; int cin2 = 0; const float *w2 = nullptr;
+  std::vector<float> scale, shift, scale2, shift2;
+  bool relu = false;
+  const __half *res = nullptr; int res_stride = 0, res_shift = 0, res_side = 0;
+  void *out1 = nullptr; bool out1_f32 = false;
+  __half *out2 = nullptr;
+};
+
+metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L) {
+  if (g.cin % kTileK != 0 || g.cin2 % kTileK != 0)
+    return fail(METRO_ERR_VALUE, "%s: input channels (%d, %d) must be multiples of %d", g.name.c_str(), g.cin, g.cin2, kTileK);
+  if (g.cout % 8 != 0) return fail(METRO_ERR_VALUE, "%s: cout %d must be a multiple of 8", g.name.c_str(), g.cout);
+  if (g.stride == 2 && (g.in_side % 2 != 0)) return fail(METRO_ERR_VALUE, "%s: stride 2 needs an even input side", g.name.c_str());
+  L = ConvGemmLaunch();
+  L.name = g.name;
+  ConvGemmParams &p = L.prm;
+  std::memset(&p, 0, sizeof p);
+  L.block_n = conv_gemm_pick_block_n(g.cout);
+  const int cout_pad = conv_gemm_cout_pad(g.cout, L.block_n);
+  p.cout = g.cout;
+  p.n_tiles = cout_pad / L.block_n;
+  metro_status st = conv_gemm_geometry(p, g.out_side);
+  if (st != METRO_OK) return st;
+  st = conv_gemm_set_taps(p, g.k, g.stride, g.rate, g.pad_lo);
+  if (st != METRO_OK) return st;
+  p.cblk0 = g.cin / kTileK;
+  p.cblk1 = g.cin2 / kTileK;
+  // weights
+  const int K = g.k * g.k * g.cin + g.cin2;
+  std::vector<__half> packed(size_t(cout_pad) * K);
+  conv_gemm_pack_weights(g.w, g.k, g.cin, g.cout, g.w2, g.cin2, cout_pad, packed.data());
+  __half *d_w = nullptr;
+  st = arena.upload(&d_w, packed);
+  if (st != METRO_OK) return st;
+  st = make_weight_tensor_map(&p.bmap, d_w, cout_pad, K, L.block_n);
+  if (st != METRO_OK) return st;
+  // activations
+  if (g.stride == 1) {
+    st = make_act_tensor_map(&p.amap[0], g.src, g.n_max, g.in_side, g.in_side, g.cin, 1, 0, 0, p.wo, p.th, p.nb);
+    if (st != METRO_OK) return st;
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        st = make_act_tensor_map(&p.amap[ph * 2 + pw], g.src, g.n_max, g.in_side, g.in_side, g.cin, 2, ph, pw, p.wo,
+                                 p.th, p.nb);
+        if (st != METRO_OK) return st;
+      }
+  }
+  if (g.cin2) {
+    st = make_act_tensor_map(&p.a2map, g.src2, g.n_max, g.out_side, g.out_side, g.cin2, 1, 0, 0, p.wo, p.th, p.nb);
+    if (st != METRO_OK) return st;
+  }
+  // epilogue vectors (padded to cout_pad so the kernel never reads out of range)
+  float *d = nullptr;
+  st = arena.upload(&d, g.scale, cout_pad); if (st != METRO_OK) return st; p.scale = d;
+  st = arena.upload(&d, g.shift, cout_pad); if (st != METRO_OK) return st; p.shift = d;
+  if (g.out2) {
+    st = arena.upload(&d, g.scale2, cout_pad); if (st != METRO_OK) return st; p.scale2 = d;
+    st = arena.upload(&d, g.shift2, cout_pad); if (st != METRO_OK) return st; p.shift2 = d;
+  }
+  p.res = g.res; p.res_stride = g.res_stride; p.res_shift = g.res_shift; p.res_h = p.res_w = g.res_side;
+  p.out1 = g.out1; p.out1_f32 = g.out1_f32 ? 1 : 0; p.relu1 = g.relu ? 1 : 0;
+  p.out2 = g.out2;
+  if (g.out1_f32 && g.out2) return fail(METRO_ERR_INTERNAL, "%s: second output needs an fp16 first output", g.name.c_str());
+  L.flops_per_img = 2.0 * g.out_side * g.out_side * double(g.cout) * K;
+  conv_gemm_set_batch(p, g.n_max);
+  return METRO_OK;
+}
+
+}  // namespace
+}  // namespace metro
+
+using namespace metro;
+
+struct metro_handle {
+  int device = 0, num_sms = 0, max_batch = 0;
+  metro_spec spec{};
+  std::vector<int32_t> perm;
+  NetPlan plan;
+  DeviceArena arena;
+  // root
+  float *d_root_w = nullptr, *d_root_b = nullptr, *d_pool_scale = nullptr, *d_pool_shift = nullptr;
+  __half *buf_root = nullptr, *pool_raw = nullptr, *pool_pre = nullptr;
+  std::vector<ConvGemmLaunch> gemms;
+  void *buf_head = nullptr;
+  SoftargmaxLaunch sam{};
+  void *sam_ws = nullptr;
+  std::map<std::string, std::pair<const void *, size_t>> debug;   // name -> (buffer, elems per crop)
+  // host-buffer path
+  cudaStream_t stream = nullptr;
+  float *stage_img = nullptr, *stage_pose = nullptr;
+};
+
+namespace {
+
+metro_status check_spec(const metro_spec *spec) {
+  if (!spec) return fail(METRO_ERR_VALUE, "spec is null");
+  if (spec->n_joints_out <= 0 || !spec->permutation) return fail(METRO_ERR_VALUE, "permutation is required");
+  if (spec->n_joints_out > kMaxJointsOut) return fail(METRO_ERR_VALUE, "n_joints_out > %d", kMaxJointsOut);
+  for (int i = 0; i < spec->n_joints_out; ++i)
+    if (spec->permutation[i] < 0 || spec->permutation[i] >= spec->n_joints_model)
+      return fail(METRO_ERR_VALUE, "permutation[%d]=%d out of range", i, spec->permutation[i]);
+  if (spec->head_dtype != METRO_F32 && spec->head_dtype != METRO_F16) return fail(METRO_ERR_VALUE, "bad head_dtype");
+  return METRO_OK;
+}
+
+metro_status build_handle(metro_handle &h, const float *blob) {
+  const NetPlan &pl = h.plan;
+  const int N = h.max_batch;
+  DeviceArena &A = h.arena;
+  const bool keep = h.spec.keep_activations != 0;
+  metro_status st;
+  auto alloc_half = [&](__half **p, size_t elems_per_img) -> metro_status {
+    void *q = nullptr;
+    metro_status s = A.alloc(&q, elems_per_img * N * sizeof(__half));
+    *p = static_cast<__half *>(q);
+    return s;
+  };
+
+  // ---- root: conv1 filters as fp16-rounded floats [147][64], bias ----
+  {
+    std::vector<float> w(147 * 64), b(64);
+    for (int i = 0; i < 147 * 64; ++i) w[i] = __half2float(__float2half_rn(blob[pl.root.w_off + i]));
+    for (int i = 0; i < 64; ++i) b[i] = blob[pl.root.b_off + i];
+    if ((st = A.upload(&h.d_root_w, w)) != METRO_OK) return st;
+    if ((st = A.upload(&h.d_root_b, b)) != METRO_OK) return st;
+    if ((st = alloc_half(&h.buf_root, size_t(pl.pool_in) * pl.pool_in * 64)) != METRO_OK) return st;
+    h.debug["conv1"] = {h.buf_root, size_t(pl.pool_in) * pl.pool_in * 64};
+  }
+  // ---- sizes of the rotating buffers ----
+  size_t raw_elems = size_t(pl.pool_out) * pl.pool_out * 64, r1_elems = 0, r2_elems = 0;
+  for (const auto &u : pl.units) {
+    raw_elems = std::max(raw_elems, size_t(u.out_side) * u.out_side * u.depth);
+    r1_elems = std::max(r1_elems, size_t(u.in_side) * u.in_side * u.cb);
+    r2_elems = std::max(r2_elems, size_t(u.out_side) * u.out_side * u.cb);
+  }
+  __half *raw[2] = {nullptr, nullptr}, *pre[2] = {nullptr, nullptr}, *r1 = nullptr, *r2 = nullptr;
+  if (!keep) {
+    for (int i = 0; i < 2; ++i) {
+      if ((st = alloc_half(&raw[i], raw_elems)) != METRO_OK) return st;
+      if ((st = alloc_half(&pre[i], raw_elems)) != METRO_OK) return st;
+    }
+    if ((st = alloc_half(&r1, r1_elems)) != METRO_OK) return st;
+    if ((st = alloc_half(&r2, r2_elems)) != METRO_OK) return st;
+  }
+  // ---- pool1 + first pre-activation ----
+  std::vector<float> sc, sf;
+  bn_affine(blob + pl.units[0].preact_off, pl.units[0].cin, sc, sf);
+  if ((st = A.upload(&h.d_pool_scale, sc)) != METRO_OK) return st;
+  if ((st = A.upload(&h.d_pool_shift, sf)) != METRO_OK) return st;
+  const size_t pool_elems = size_t(pl.pool_out) * pl.pool_out * 64;
+  __half *cur_raw, *cur_pre;
+  if (keep) {
+    if ((st = alloc_half(&cur_raw, pool_elems)) != METRO_OK) return st;
+    if ((st = alloc_half(&cur_pre, pool_elems)) != METRO_OK) return st;
+  } else { cur_raw = raw[0]; cur_pre = pre[0]; }
+  h.pool_raw = cur_raw; h.pool_pre = cur_pre;
+  h.debug["pool1"] = {cur_raw, pool_elems};
+
+  // ---- residual units ----
+  for (size_t i = 0; i < pl.units.size(); ++i) {
+    const UnitPlan &u = pl.units[i];
+    const bool last = (i + 1 == pl.units.size());
+    if (u.proj && u.stride != 1)
+      return fail(METRO_ERR_INTERNAL, "%s: strided projection shortcut is not part of ResNet-50/101", u.name.c_str());
+    __half *b1 = r1, *b2 = r2, *nraw = raw[(i + 1) & 1], *npre = pre[(i + 1) & 1];
+    const size_t e1 = size_t(u.in_side) * u.in_side * u.cb, e2 = size_t(u.out_side) * u.out_side * u.cb;
+    const size_t eo = size_t(u.out_side) * u.out_side * u.depth;
+    if (keep) {
+      if ((st = alloc_half(&b1, e1)) != METRO_OK) return st;
+      if ((st = alloc_half(&b2, e2)) != METRO_OK) return st;
+      if ((st = alloc_half(&nraw, eo)) != METRO_OK) return st;
+      if ((st = alloc_half(&npre, eo)) != METRO_OK) return st;
+    }
+    ConvGemmLaunch L;
+    // conv1: 1x1, BN, ReLU on the pre-activation (resnet_v2.py:127-128)
+    {
+      GemmSpec g; g.name = u.conv1.name; g.n_max = N; g.src = cur_pre; g.in_side = u.in_side; g.cin = u.cin;
+      g.out_side = u.in_side; g.cout = u.cb; g.w = blob + u.conv1.w_off;
+      bn_affine(blob + u.conv1.bn_off, u.cb, g.scale, g.shift);
+      g.relu = true; g.out1 = b1;
+      if ((st = build_gemm(A, g, L)) != METRO_OK) return st;
+      h.gemms.push_back(L);
+      h.debug[u.name + "/conv1"] = {b1, e1};
+    }
+    // conv2: 3x3 stride/rate/centred, BN, ReLU (resnet_v2.py:130-132)
+    {
+      GemmSpec g; g.name = u.conv2.name; g.n_max = N; g.src = b1; g.in_side = u.in_side; g.cin = u.cb;
+      g.k = 3; g.stride = u.stride; g.rate = u.rate; g.pad_lo = u.conv2.pad_lo;
+      g.out_side = u.out_side; g.cout = u.cb; g.w = blob + u.conv2.w_off;
+      bn_affine(blob + u.conv2.bn_off, u.cb, g.scale, g.shift);
+      g.relu = true; g.out1 = b2;
+      if ((st = build_gemm(A, g, L)) != METRO_OK) return st;
+      h.gemms.push_back(L);
+      h.debug[u.name + "/conv2"] = {b2, e2};
+    }
+    // conv3 (+ projection shortcut as a second K range) + bias(es) + identity residual -> raw sum and
+    // the next unit's pre-activation / postnorm (resnet_v2.py:119-125,134-138,229)
+    {
+      GemmSpec g; g.name = u.conv3.name; g.n_max = N; g.src = b2; g.in_side = u.out_side; g.cin = u.cb;
+      g.out_side = u.out_side; g.cout = u.depth; g.w = blob + u.conv3.w_off;
+      g.scale.assign(u.depth, 1.0f);
+      g.shift.assign(blob + u.conv3.b_off, blob + u.conv3.b_off + u.depth);
+      if (u.proj) {
+        g.src2 = cur_pre; g.cin2 = u.cin; g.w2 = blob + u.shortcut.w_off;
+        for (int c = 0; c < u.depth; ++c) g.shift[c] = float(double(g.shift[c]) + double(blob[u.shortcut.b_off + c]));
+      } else {
+        g.res = cur_raw; g.res_stride = u.stride; g.res_shift = u.shift; g.res_side = u.in_side;
+      }
+      const bool need_raw = keep || (!last && !pl.units[i + 1].proj);
+      g.out1 = need_raw ? nraw : nullptr;
+      g.out2 = npre;
+      const int64_t next_bn = last ? pl.postnorm_off : pl.units[i + 1].preact_off;
+      bn_affine(blob + next_bn, u.depth, g.scale2, g.shift2);
+      if ((st = build_gemm(A, g, L)) != METRO_OK) return st;
+      h.gemms.push_back(L);
+      h.debug[u.name + "/out"] = {need_raw ? nraw : nullptr, eo};
+      h.debug[u.name + "/pre"] = {npre, eo};
+    }
+    cur_raw = nraw; cur_pre = npre;
+  }
+  // ---- logits (resnet_v2.py:234-236) -> head tensor ----
+  {
+    const size_t eh = size_t(pl.feat_side) * pl.feat_side * pl.logits.cout;
+    const bool f16 = h.spec.head_dtype == METRO_F16;
+    if ((st = A.alloc(&h.buf_head, eh * N * (f16 ? 2 : 4))) != METRO_OK) return st;
+    GemmSpec g; g.name = "logits"; g.n_max = N; g.src = cur_pre; g.in_side = pl.feat_side; g.cin = pl.feat_channels;
+    g.out_side = pl.feat_side; g.cout = pl.logits.cout; g.w = blob + pl.logits.w_off;
+    g.scale.assign(g.cout, 1.0f);
+    g.shift.assign(blob + pl.logits.b_off, blob + pl.logits.b_off + g.cout);
+    g.out1 = h.buf_head; g.out1_f32 = !f16;
+    ConvGemmLaunch L;
+    if ((st = build_gemm(A, g, L)) != METRO_OK) return st;
+    h.gemms.push_back(L);
+    h.debug["head"] = {h.buf_head, eh};
+  }
+  // ---- soft-argmax ----
+  {
+    metro_softargmax_desc d{};
+    d.side = pl.feat_side; d.n_joints_model = pl.n_joints; d.depth = pl.depth; d.stride = pl.stride;
+    d.centered_stride = pl.centered; d.proc_side = pl.proc_side; d.box_size_mm = h.spec.box_size_mm;
+    d.n_joints_out = int(h.perm.size()); d.permutation = h.perm.data(); d.head_dtype = h.spec.head_dtype;
+    if ((st = softargmax_plan(d, N, h.sam)) != METRO_OK) return st;
+    const size_t ws = softargmax_workspace_bytes(h.sam);
+    if ((st = A.alloc(&h.sam_ws, ws)) != METRO_OK) return st;
+    METRO_CUDA(cudaMemset(h.sam_ws, 0, ws));
+  }
+  METRO_CUDA(cudaDeviceSynchronize());
+  return METRO_OK;
+}
+
+struct Timer {
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+};
+
+metro_status run(metro_handle *h, const void *images, bool u8, int n, float *poses, cudaStream_t s, Timer *t) {
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  if (n < 0 || n > h->max_batch) return fail(METRO_ERR_VALUE, "batch %d outside [0, max_batch=%d]", n, h->max_batch);
+  if (n == 0) return METRO_OK;
+  if (!images || !poses) return fail(METRO_ERR_VALUE, "null image / pose buffer");
+  METRO_CUDA(cudaSetDevice(h->device));
+  const NetPlan &pl = h->plan;
+  metro_status st;
+  auto mark = [&](const char *name) {
+    if (!t) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+    t->ev.push_back(e); t->names.push_back(name);
+  };
+  mark("start");
+  if ((st = root_conv_launch(images, u8, h->d_root_w, h->d_root_b, h->buf_root, n, pl.proc_side, pl.pool_in, s)) != METRO_OK) return st;
+  mark("conv1");
+  if ((st = pool_preact_launch(h->buf_root, h->pool_raw, h->pool_pre, h->d_pool_scale, h->d_pool_shift, n, pl.pool_in,
+                               pl.pool_out, 64, s)) != METRO_OK) return st;
+  mark("pool1");
+  for (auto &L : h->gemms) {
+    conv_gemm_set_batch(L.prm, n);
+    if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
+    mark(L.name.c_str());
+  }
+  SoftargmaxLaunch sl = h->sam;
+  sl.n = n; sl.head = h->buf_head; sl.out = poses;
+  sl.counters = static_cast<unsigned int *>(h->sam_ws);
+  sl.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(h->sam_ws) +
+                                           ((size_t(h->max_batch) * 4 + 255) & ~size_t(255)));
+  if ((st = softargmax_launch(sl, s)) != METRO_OK) return st;
+  mark("softargmax");
+  return METRO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *metro_last_error(void) { return g_last_error.c_str(); }
+const char *metro_version(void) { return "metro-b200 0.1 (sm_100a)"; }
+
+metro_status metro_blob_floats(const metro_spec *spec, uint64_t *n_floats) {
+  if (!spec || !n_floats) return fail(METRO_ERR_VALUE, "null argument");
+  NetPlan pl; std::string err;
+  const metro_status st = build_plan(*spec, pl, err);
+  if (st != METRO_OK) return fail(st, "%s", err.c_str());
+  *n_floats = uint64_t(pl.blob_floats);
+  return METRO_OK;
+}
+
+metro_status metro_plan_describe(const metro_spec *spec, char *buf, size_t buf_bytes, size_t *needed) {
+  if (!spec) return fail(METRO_ERR_VALUE, "null argument");
+  NetPlan pl; std::string err;
+  const metro_status st = build_plan(*spec, pl, err);
+  if (st != METRO_OK) return fail(st, "%s", err.c_str());
+  const std::string js = plan_to_json(pl);
+  if (needed) *needed = js.size() + 1;
+  if (buf && buf_bytes > 0) {
+    const size_t n = std::min(buf_bytes - 1, js.size());
+    std::memcpy(buf, js.data(), n);
+    buf[n] = 0;
+  }
+  return METRO_OK;
+}
+
+metro_status metro_create(const metro_spec *spec, const float *weights_blob, uint64_t n_floats, int32_t device,
+                          metro_handle **out) {
+  if (!out) return fail(METRO_ERR_VALUE, "out is null");
+  *out = nullptr;
+  metro_status st = check_spec(spec);
+  if (st != METRO_OK) return st;
+  if (spec->max_batch <= 0) return fail(METRO_ERR_VALUE, "max_batch must be positive");
+  std::unique_ptr<metro_handle> h(new metro_handle());
+  std::string err;
+  st = build_plan(*spec, h->plan, err);
+  if (st != METRO_OK) return fail(st, "%s", err.c_str());
+  if (!weights_blob || n_floats != uint64_t(h->plan.blob_floats))
+    return fail(METRO_ERR_VALUE, "weight blob has %llu floats, the model needs %lld", (unsigned long long)n_floats,
+                (long long)h->plan.blob_floats);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(METRO_ERR_NO_DEVICE, "no CUDA device: libmetro has no CPU fallback");
+  if (device < 0 || device >= count) return fail(METRO_ERR_VALUE, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  METRO_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(METRO_ERR_NO_DEVICE, "device %d is sm_%d%d; libmetro is built for sm_100a only", device, prop.major, prop.minor);
+  METRO_CUDA(cudaSetDevice(device));
+  h->device = device; h->num_sms = prop.multiProcessorCount; h->max_batch = spec->max_batch;
+  h->spec = *spec;
+  h->perm.assign(spec->permutation, spec->permutation + spec->n_joints_out);
+  h->spec.permutation = h->perm.data();
+  st = build_handle(*h, weights_blob);
+  if (st != METRO_OK) return st;
+  *out = h.release();
+  return METRO_OK;
+}
+
+metro_status metro_destroy(metro_handle *h) {
+  if (!h) return METRO_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stage_img) cudaFree(h->stage_img);
+  if (h->stage_pose) cudaFree(h->stage_pose);
+  delete h;
+  return METRO_OK;
+}
+
+metro_status metro_workspace_bytes(const metro_handle *h, uint64_t *bytes) {
+  if (!h || !bytes) return fail(METRO_ERR_VALUE, "null argument");
+  *bytes = h->arena.total;
+  return METRO_OK;
+}
+
+metro_status metro_infer(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev, void *stream) {
+  return run(h, images_dev, false, n, poses_dev, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+metro_status metro_infer_u8(metro_handle *h, const uint8_t *images_u8_dev, int32_t n, float *poses_dev, void *stream) {
+  return run(h, images_u8_dev, true, n, poses_dev, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+metro_status metro_infer_host(metro_handle *h, const float *images_host, int32_t n, float *poses_host) {
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  if (n < 0 || n > h->max_batch) return fail(METRO_ERR_VALUE, "batch %d outside [0, max_batch=%d]", n, h->max_batch);
+  if (n == 0) return METRO_OK;
+  if (!images_host || !poses_host) return fail(METRO_ERR_VALUE, "null image / pose buffer");
+  METRO_CUDA(cudaSetDevice(h->device));
+  const size_t img_bytes = size_t(h->plan.proc_side) * h->plan.proc_side * 3 * sizeof(float);
+  const size_t pose_bytes = h->perm.size() * 3 * sizeof(float);
+  if (!h->stream) {
+    METRO_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    METRO_CUDA(cudaMalloc(&h->stage_img, img_bytes * h->max_batch));
+    METRO_CUDA(cudaMalloc(&h->stage_pose, pose_bytes * h->max_batch));
+  }
+  METRO_CUDA(cudaMemcpyAsync(h->stage_img, images_host, img_bytes * n, cudaMemcpyHostToDevice, h->stream));
+  const metro_status st = run(h, h->stage_img, false, n, h->stage_pose, h->stream, nullptr);
+  if (st != METRO_OK) return st;
+  METRO_CUDA(cudaMemcpyAsync(poses_host, h->stage_pose, pose_bytes * n, cudaMemcpyDeviceToHost, h->stream));
+  METRO_CUDA(cudaStreamSynchronize(h->stream));
+  return METRO_OK;
+}
+
+metro_status metro_softargmax_workspace_bytes(const metro_softargmax_desc *d, int32_t n, uint64_t *bytes) {
+  if (!d || !bytes) return fail(METRO_ERR_VALUE, "null argument");
+  SoftargmaxLaunch L;
+  const metro_status st = softargmax_plan(*d, n, L);
+  if (st != METRO_OK) return st;
+  *bytes = softargmax_workspace_bytes(L);
+  return METRO_OK;
+}
+
+metro_status metro_softargmax(const metro_softargmax_desc *d, const void *head_dev, int32_t n, float *poses_dev,
+                              void *workspace_dev, void *stream) {
+  if (!d) return fail(METRO_ERR_VALUE, "null argument");
+  SoftargmaxLaunch L;
+  metro_status st = softargmax_plan(*d, n, L);
+  if (st != METRO_OK) return st;
+  if (n == 0) return METRO_OK;
+  if (!head_dev || !poses_dev || !workspace_dev) return fail(METRO_ERR_VALUE, "null device buffer");
+  L.head = head_dev; L.out = poses_dev;
+  L.counters = static_cast<unsigned int *>(workspace_dev);
+  L.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace_dev) + ((size_t(n) * 4 + 255) & ~size_t(255)));
+  return softargmax_launch(L, static_cast<cudaStream_t>(stream));
+}
+
+metro_status metro_conv2d(const metro_conv_desc *d, const void *x_dev, const float *w_host, const void *x2_dev,
+                          const float *w2_host, const float *scale_host, const float *shift_host, const void *res_dev,
+                          void *y_dev, const float *scale2_host, const float *shift2_host, void *y2_dev, int32_t device,
+                          void *stream) {
+  if (!d || !x_dev || !w_host || !scale_host || !shift_host) return fail(METRO_ERR_VALUE, "null argument");
+  if (d->k != 1 && d->k != 3) return fail(METRO_ERR_VALUE, "metro_conv2d: k must be 1 or 3");
+  if (d->n <= 0) return fail(METRO_ERR_VALUE, "metro_conv2d: n must be positive");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(METRO_ERR_NO_DEVICE, "no CUDA device: libmetro has no CPU fallback");
+  cudaDeviceProp prop;
+  METRO_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(METRO_ERR_NO_DEVICE, "device is sm_%d%d; sm_100a required", prop.major, prop.minor);
+  METRO_CUDA(cudaSetDevice(device));
+  const int k_eff = d->k + (d->k - 1) * (d->rate - 1);
+  const int pad_total = (d->stride == 1) ? (k_eff - 1) : -1;
+  int out_side;
+  if (d->stride == 1) out_side = d->in_side + pad_total - k_eff + 1;  // SAME
+  else out_side = d->in_side / d->stride;
+  DeviceArena arena;
+  GemmSpec g; g.name = "metro_conv2d"; g.n_max = d->n;
+  g.src = static_cast<const __half *>(x_dev); g.in_side = d->in_side; g.cin = d->cin;
+  g.k = d->k; g.stride = d->stride; g.rate = d->rate; g.pad_lo = d->pad_lo; g.out_side = out_side; g.cout = d->cout;
+  g.w = w_host;
+  if (d->cin2 > 0) { g.src2 = static_cast<const __half *>(x2_dev); g.cin2 = d->cin2; g.w2 = w2_host; }
+  g.scale.assign(scale_host, scale_host + d->cout);
+  g.shift.assign(shift_host, shift_host + d->cout);
+  g.relu = d->relu != 0;
+  if (res_dev && d->res_stride > 0) {
+    g.res = static_cast<const __half *>(res_dev); g.res_stride = d->res_stride; g.res_shift = d->res_shift;
+    g.res_side = out_side * d->res_stride;
+  }
+  g.out1 = y_dev; g.out1_f32 = d->out_dtype == METRO_F32;
+  if (y2_dev) {
+    if (!scale2_host || !shift2_host) return fail(METRO_ERR_VALUE, "metro_conv2d: y2 needs scale2/shift2");
+    g.out2 = static_cast<__half *>(y2_dev);
+    g.scale2.assign(scale2_host, scale2_host + d->cout);
+    g.shift2.assign(shift2_host, shift2_host + d->cout);
+  }
+  ConvGemmLaunch L;
+  metro_status st = build_gemm(arena, g, L);
+  if (st != METRO_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  st = conv_gemm_launch(L, prop.multiProcessorCount, s);
+  if (st != METRO_OK) return st;
+  METRO_CUDA(cudaStreamSynchronize(s));   // temporaries (packed weights) are freed on return
+  return METRO_OK;
+}
+
+metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf, uint64_t buf_bytes, uint64_t *elems) {
+  if (!h || !name) return fail(METRO_ERR_VALUE, "null argument");
+  auto it = h->debug.find(name);
+  if (it == h->debug.end() || !it->second.first) return fail(METRO_ERR_VALUE, "no activation named '%s'", name);
+  const bool is_head = std::string(name) == "head";
+  const size_t esize = is_head ? (h->spec.head_dtype == METRO_F16 ? 2 : 4) : 2;
+  const uint64_t n_el = uint64_t(it->second.second) * h->max_batch;
+  if (elems) *elems = n_el;
+  if (host_buf) {
+    if (buf_bytes < n_el * esize) return fail(METRO_ERR_VALUE, "buffer too small: need %llu bytes", (unsigned long long)(n_el * esize));
+    METRO_CUDA(cudaSetDevice(h->device));
+    METRO_CUDA(cudaDeviceSynchronize());
+    METRO_CUDA(cudaMemcpy(host_buf, it->second.first, n_el * esize, cudaMemcpyDeviceToHost));
+  }
+  return METRO_OK;
+}
+
+metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launches) {
+  if (!h || !launches) return fail(METRO_ERR_VALUE, "null argument");
+  *launches = n > 0 ? int32_t(h->gemms.size()) + 3 : 0;
+  return METRO_OK;
+}
+
+metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev, float *ms_out,
+                           char *names_buf, size_t names_bytes, int32_t *n_launches) {
+  Timer t;
+  METRO_CUDA(cudaDeviceSynchronize());
+  metro_status st = run(h, images_dev, false, n, poses_dev, nullptr, &t);
+  if (st != METRO_OK) return st;
+  METRO_CUDA(cudaDeviceSynchronize());
+  std::string names;
+  const int cnt = int(t.ev.size()) - 1;
+  for (int i = 0; i < cnt; ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]);
+    if (ms_out) ms_out[i] = ms;
+    names += t.names[i + 1];
+    names += '\n';
+  }
+  for (auto e : t.ev) cudaEventDestroy(e);
+  if (n_launches) *n_launches = cnt;
+  if (names_buf && names_bytes) {
+    const size_t k = std::min(names_bytes - 1, names.size());
+    std::memcpy(names_buf, names.data(), k);
+    names_buf[k] = 0;
+  }
+  return METRO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference's inference contract on top of libmetro.so.
+
+Reference: ``inference.py:31-43`` --
+
+    poses, edges, joint_names = estimate_pose(images_tensor, model_path)
+
+where the frozen graph maps 'input:0' (float32 NHWC [N,256,256,3] in [0,1]) to 'output'
+(float32 [N,J,3] root-relative millimetres) and carries the 'joint_edges' / 'joint_names' constants
+(src/main.py:106-161).  Here a ``MetroModel`` plays the role of the frozen graph; torch tensors are
+used only as device-buffer containers (``data_ptr()``) and for the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import lib as _lib
+from .joints import exported_joint_info, export_permutation, model_joint_info
+from .spec import NetSpec
+from .weights import blob_size, pack_blob, synth_weights
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class MetroModel:
+    """One exported model resident on one GPU (== the imported GraphDef + its weight constants)."""
+
+    def __init__(self, arch: str = 'resnet_v2_50', stride: int = 16, dataset: str = 'h36m',
+                 weights=None, max_batch: int = 256, device: int = 0, head_dtype: str = 'f32',
+                 keep_activations: bool = False, seed: int = 0, n_joints_model: Optional[int] = None,
+                 permutation: Optional[Sequence[int]] = None):
+        self.lib = _lib.load()
+        self.dataset = dataset
+        ji = model_joint_info(dataset)
+        self.n_joints_model = n_joints_model or ji.n_joints
+        self.permutation = list(permutation) if permutation is not None else export_permutation(dataset)
+        self.joint_info = exported_joint_info(dataset) if permutation is None else None
+        self.spec = NetSpec(arch, stride, self.n_joints_model)      # raises ValueError like the reference
+        self.device = device
+        self.max_batch = max_batch
+        self.head_dtype = {'f32': _lib.METRO_F32, 'f16': _lib.METRO_F16}[head_dtype]
+        self._cspec = _lib.make_spec(arch, stride, self.n_joints_model, self.permutation, max_batch,
+                                     head_dtype=self.head_dtype, keep_activations=keep_activations)
+        if weights is None:
+            weights = synth_weights(self.spec, seed)
+        blob = weights if isinstance(weights, np.ndarray) else pack_blob(self.spec, weights)
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        if blob.size != blob_size(self.spec):
+            raise ValueError(f'weight blob has {blob.size} floats, the model needs {blob_size(self.spec)}')
+        h = C.c_void_p()
+        _lib.check(self.lib.metro_create(C.byref(self._cspec), blob.ctypes.data_as(C.c_void_p), blob.size,
+                                         device, C.byref(h)))
+        self._h = h
+
+    # -- the three fetches of the frozen graph ----------------------------------------------------
+    @property
+    def joint_names(self):
+        return list(self.joint_info.names)
+
+    @property
+    def joint_edges(self) -> np.ndarray:
+        return np.asarray(self.joint_info.edges, dtype=np.int64)
+
+    @property
+    def n_joints_out(self) -> int:
+        return len(self.permutation)
+
+    def infer(self, images, out=None, stream: Optional[int] = None):
+        """images: CUDA float32 (or uint8) tensor NHWC [n,256,256,3]; returns CUDA float32 [n,J,3].
+        Asynchronous on the current torch stream."""
+        torch = _torch()
+        if images.dim() != 4 or tuple(images.shape[1:]) != (self.spec.proc_side, self.spec.proc_side, 3):
+            raise ValueError(f'expected [N,{self.spec.proc_side},{self.spec.proc_side},3] NHWC, got {tuple(images.shape)}')
+        if images.dtype not in (torch.float32, torch.uint8):
+            raise ValueError(f'expected float32 or uint8 images, got {images.dtype}')
+        if not images.is_cuda or images.device.index != self.device:
+            raise ValueError(f'images must live on cuda:{self.device}')
+        images = images.contiguous()
+        n = images.shape[0]
+        if out is None:
+            out = torch.empty((n, self.n_joints_out, 3), dtype=torch.float32, device=images.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(images.device).cuda_stream
+        fn = self.lib.metro_infer_u8 if images.dtype == torch.uint8 else self.lib.metro_infer
+        _lib.check(fn(self._h, images.data_ptr(), n, out.data_ptr(), stream))
+        return out
+
+    def infer_host(self, images: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host buffers in / out (what ``sess.run`` does for numpy feeds, inference.py:26-27)."""
+        if hasattr(images, 'numpy'):            # CPU torch tensor (possibly pinned): zero-copy view
+            images = images.numpy()
+        if images.ndim != 4 or images.shape[1:] != (self.spec.proc_side, self.spec.proc_side, 3):
+            raise ValueError(f'expected [N,{self.spec.proc_side},{self.spec.proc_side},3] NHWC, got {images.shape}')
+        if images.dtype != np.float32:
+            raise ValueError(f'expected float32 images, got {images.dtype}')
+        images = np.ascontiguousarray(images)
+        n = images.shape[0]
+        if out is None:
+            out = np.empty((n, self.n_joints_out, 3), dtype=np.float32)
+        elif hasattr(out, 'numpy'):
+            out = out.numpy()
+        _lib.check(self.lib.metro_infer_host(self._h, images.ctypes.data_as(C.c_void_p), n,
+                                             out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def __call__(self, images):
+        if isinstance(images, np.ndarray):
+            return self.infer_host(images)
+        if not images.is_cuda:
+            return self.infer_host(images)
+        return self.infer(images)
+
+    # -- introspection ----------------------------------------------------------------------------
+    def debug_read(self, name: str) -> np.ndarray:
+        n = C.c_uint64(0)
+        _lib.check(self.lib.metro_debug_read(self._h, name.encode(), None, 0, C.byref(n)))
+        dt = np.float16
+        if name == 'head' and self.head_dtype == _lib.METRO_F32:
+            dt = np.float32
+        buf = np.empty(n.value, dtype=dt)
+        _lib.check(self.lib.metro_debug_read(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes, None))
+        return buf.reshape(self.max_batch, -1)
+
+    def profile(self, images, out=None):
+        torch = _torch()
+        n = images.shape[0]
+        if out is None:
+            out = torch.empty((n, self.n_joints_out, 3), dtype=torch.float32, device=images.device)
+        cnt = self.launch_count(n)
+        ms = (C.c_float * (cnt + 4))()
+        names = C.create_string_buffer(64 * (cnt + 4))
+        k = C.c_int32(0)
+        _lib.check(self.lib.metro_profile(self._h, images.data_ptr(), n, out.data_ptr(), ms, names, len(names), C.byref(k)))
+        return list(zip(names.value.decode().split('\n'), list(ms)[:k.value]))
+
+    def launch_count(self, n: int) -> int:
+        k = C.c_int32(0)
+        _lib.check(self.lib.metro_launch_count(self._h, n, C.byref(k)))
+        return k.value
+
+    def workspace_bytes(self) -> int:
+        n = C.c_uint64(0)
+        _lib.check(self.lib.metro_workspace_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.metro_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def estimate_pose(images, model: MetroModel) -> Tuple[object, np.ndarray, list]:
+    """Mirror of ``estimate_pose(images_tensor, model_path)`` (inference.py:31-43): returns
+    (poses [N,J,3] mm, joint_edges [E,2] int64, joint_names [J])."""
+    return model(images), model.joint_edges, model.joint_names
+
+
+class SoftArgmax:
+    """Stand-alone heatmap decode (volumetric.py:227-235,288-306; tfu3d.py:23-25; main.py:127)."""
+
+    def __init__(self, side: int, n_joints_model: int, stride: int, permutation: Sequence[int], depth: int = 8,
+                 centered_stride: bool = True, proc_side: int = 256, box_size_mm: float = 2200.0,
+                 head_dtype: str = 'f32', splits: int = 0, lanes: int = 0):
+        self.lib = _lib.load()
+        self.perm = (C.c_int32 * len(permutation))(*permutation)
+        self.n_out = len(permutation)
+        self.desc = _lib.SoftargmaxDesc(side, n_joints_model, depth, stride, int(centered_stride), proc_side,
+                                        box_size_mm, len(permutation), C.cast(self.perm, C.POINTER(C.c_int32)),
+                                        {'f32': 0, 'f16': 1}[head_dtype], splits, lanes)
+        self.side, self.channels = side, depth * n_joints_model
+        self.head_dtype = head_dtype
+        self._ws = None
+        self._ws_n = -1
+
+    def workspace_bytes(self, n: int) -> int:
+        b = C.c_uint64(0)
+        _lib.check(self.lib.metro_softargmax_workspace_bytes(C.byref(self.desc), n, C.byref(b)))
+        return b.value
+
+    def __call__(self, head, out=None):
+        torch = _torch()
+        want = torch.float32 if self.head_dtype == 'f32' else torch.float16
+        if head.dim() != 4 or tuple(head.shape[1:]) != (self.side, self.side, self.channels):
+            raise ValueError(f'expected NHWC [N,{self.side},{self.side},{self.channels}], got {tuple(head.shape)}')
+        if head.dtype != want or not head.is_cuda:
+            raise ValueError(f'expected a CUDA {want} tensor')
+        head = head.contiguous()
+        n = head.shape[0]
+        if self._ws is None or self._ws_n != n:
+            self._ws = torch.zeros(max(self.workspace_bytes(n), 16), dtype=torch.uint8, device=head.device)
+            self._ws_n = n
+        if out is None:
+            out = torch.empty((n, self.n_out, 3), dtype=torch.float32, device=head.device)
+        stream = torch.cuda.current_stream(head.device).cuda_stream
+        _lib.check(self.lib.metro_softargmax(C.byref(self.desc), head.data_ptr(), n, out.data_ptr(),
+                                             self._ws.data_ptr(), stream))
+        return out
+
+
+def conv2d(x, w_hwio: np.ndarray, scale: np.ndarray, shift: np.ndarray, stride: int = 1, rate: int = 1,
+           pad_lo: Optional[int] = None, relu: bool = False, out_dtype: str = 'f16', res=None, res_stride: int = 0,
+           res_shift: int = 0, x2=None, w2: Optional[np.ndarray] = None, scale2=None, shift2=None):
+    """Operator-level entry to the fused tcgen05 convolution (metro_conv2d); x: CUDA fp16 NHWC."""
+    torch = _torch()
+    lib = _lib.load()
+    n, side, _, cin = x.shape
+    k = w_hwio.shape[0]
+    cout = w_hwio.shape[3]
+    k_eff = k + (k - 1) * (rate - 1)
+    if pad_lo is None:
+        pad_lo = (k_eff - 1) // 2
+    out_side = side if stride == 1 else side // stride
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    w_hwio, scale, shift = f32(w_hwio), f32(scale), f32(shift)
+    cin2 = 0 if x2 is None else x2.shape[3]
+    d = _lib.ConvDesc(n, side, cin, cout, k, stride, rate, pad_lo, int(relu), 0 if out_dtype == 'f32' else 1,
+                      res_stride if res is not None else 0, res_shift, cin2)
+    y = torch.empty((n, out_side, out_side, cout), dtype=torch.float32 if out_dtype == 'f32' else torch.float16,
+                    device=x.device)
+    y2 = None
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    if scale2 is not None:
+        scale2, shift2 = f32(scale2), f32(shift2)
+        y2 = torch.empty((n, out_side, out_side, cout), dtype=torch.float16, device=x.device)
+    if w2 is not None:
+        w2 = f32(w2)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(lib.metro_conv2d(C.byref(d), x.data_ptr(), p(w_hwio), None if x2 is None else x2.data_ptr(), p(w2),
+                                p(scale), p(shift), None if res is None else res.data_ptr(), y.data_ptr(),
+                                p(scale2), p(shift2), None if y2 is None else y2.data_ptr(), x.device.index or 0, stream))
+    return (y, y2) if y2 is not None else y
