@@ -1,0 +1,316 @@
+#!/usr/bin/env python3
+"""Benchmark of the MeTRo inference hot path on B200 (BASELINE.json metric: 256x256 crops/sec;
+soft-argmax HBM GB/s vs measured peak).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config B|D|A|C|E]
+
+A step = one pass of the hot path (crops -> [N,J,3] mm) over one synthetic batch.  At N=1 the
+workload is BASELINE config B (ResNet-50, stride 16, 17 joints, batch 256); with torchrun every rank
+runs the same per-GPU batch on its own shard (weak scaling) and the step ends with the all-gather of
+the results.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+from metro_pose3d_b200.joints import export_permutation, model_joint_info
+from metro_pose3d_b200.spec import CONFIGS, NetSpec
+from metro_pose3d_b200.weights import synth_head, synth_images, synth_weights
+
+METRIC = '256x256 crops/sec'
+UNIT = 'crops/s'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
+    return 6650.0, 1590.0, 1400.0, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self._stop_evt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                      '-i', str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(',')]
+                if len(f) >= 8:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        mx = [float(s[2]) for s in self.samples if s[2].replace('.', '').isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.samples)}
+
+
+def cpu_oracle_rate(spec, weights, dataset, n_sample, threads, repeats=1):
+    """crops/s of the CPU restatement of the reference graph (torch-CPU fp32) -- NOT TF 1.13."""
+    import torch
+    from oracle.metro_oracle import OracleNet      # the one place bench.py may execute oracle/
+    torch.set_num_threads(threads)
+    net = OracleNet(spec, weights, export_permutation(dataset), 'fp32')
+    img = synth_images(n_sample, seed=7)
+    net(img[:1])                                   # warm-up (oneDNN primitive creation)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        net(img)
+    dt = (time.perf_counter() - t0) / repeats
+    return n_sample / dt, dt
+
+
+def run_reference(args, cfg_name, arch, stride, dataset, batch):
+    """--impl reference: the reference's CPU path.  TensorFlow 1.13.1 cannot be installed here
+    (BASELINE.md section 4), so this times the oracle port of the same graph on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    j = model_joint_info(dataset).n_joints
+    spec = NetSpec(arch, stride, j)
+    w = synth_weights(spec, 0)
+    cores = os.cpu_count() or 1
+    sample = max(1, min(batch, 8))
+    import torch
+    from oracle.metro_oracle import OracleNet
+    torch.set_num_threads(cores)
+    net = OracleNet(spec, w, export_permutation(dataset), 'fp32')
+    img = synth_images(sample, seed=7)
+    for _ in range(max(1, min(args.warmup, 2))):
+        net(img[:1])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net(img)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'config {cfg_name}: {arch} stride_{stride} {j} joints, batch {batch}/GPU',
+                   'note': 'CPU restatement of the reference graph (torch-CPU fp32 oracle port), not TF 1.13'},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{sample} crops per step x {args.steps} steps'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='B', choices=list(CONFIGS))
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the config\'s)')
+    ap.add_argument('--head-dtype', default='f32', choices=['f32', 'f16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layers', action='store_true', help='also print per-layer timings to stderr')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    arch, stride, dataset, cfg_batch, cfg_gpus = CONFIGS[args.config]
+    per_gpu = args.batch or (cfg_batch // max(cfg_gpus, 1) if cfg_gpus > 1 else cfg_batch)
+    if args.impl == 'reference':
+        return run_reference(args, args.config, arch, stride, dataset, per_gpu)
+
+    import torch
+    import torch.distributed as dist
+    from metro_pose3d_b200.dist import ShardedPoseEstimator
+    from metro_pose3d_b200.inference import MetroModel, SoftArgmax
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a B200: the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    hbm_peak, tf_burst, tf_sust, peak_src = load_peaks()
+
+    j = model_joint_info(dataset).n_joints
+    spec = NetSpec(arch, stride, j)
+    weights = synth_weights(spec, 0)
+    model = MetroModel(arch, stride, dataset, weights=weights, max_batch=per_gpu, device=local_rank,
+                       head_dtype=args.head_dtype)
+    est = ShardedPoseEstimator(model.infer, model.n_joints_out)
+    n = per_gpu
+    # synthetic crops, uniform [0,1), generated ON the device, seed 1000 + rank.  Two input
+    # sets are rotated; one set (n * 786 KB = 201 MB at n=256) already exceeds the 126 MB L2.
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    inputs = [torch.rand((n, 256, 256, 3), generator=g, device=dev, dtype=torch.float32) for _ in range(2)]
+    out = torch.empty((n, model.n_joints_out, 3), dtype=torch.float32, device=dev)
+
+    def step(i):
+        local = model.infer(inputs[i & 1], out=out)
+        return est.gather(local, n * world)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        res = step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n * world / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host float32 in, host poses out ----
+    host_in = torch.rand((n, 256, 256, 3), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((n, model.n_joints_out, 3), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        model.infer_host(host_in, host_out)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.infer_host(host_in, host_out)
+        if world > 1:
+            est.gather(torch.from_numpy(host_out.numpy()).to(dev), n * world)
+            torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {'value': n * world / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(host_in.numel() * 4),
+           'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': e2e_ms}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (conv_gemm_kernel: every tcgen05 convolution launch) ----
+    # per-launch device times come from CUDA events recorded between launches on the launch stream
+    model.profile(inputs[0])
+    acc = {}
+    reps = 5
+    for _ in range(reps):
+        for name, t_ms in model.profile(inputs[1]):
+            acc[name] = acc.get(name, 0.0) + t_ms / reps
+    conv_ms = sum(v for k, v in acc.items() if k not in ('conv1', 'pool1', 'softargmax'))
+    gemm_convs = [c for c in spec.convs if c.name != 'conv1']
+    # algorithmic FLOPs: 2*Ho*Wo*Cout*Cin*k^2 per conv per crop; root conv1 runs on CUDA cores
+    gemm_flops = sum(c.flops for c in gemm_convs) * n
+    achieved_tf = gemm_flops / (conv_ms * 1e-3) / 1e12
+    roofline = {'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all %d launches)' % len([k for k in acc if k not in ('conv1', 'pool1', 'softargmax')]),
+                'bound': 'tensor', 'achieved': achieved_tf, 'peak': tf_sust, 'unit': 'TFLOP/s',
+                'frac': achieved_tf / tf_sust, 'traffic': None, 'peak_source': f'{peak_src} bf16 sustained',
+                'ms_per_step': conv_ms, 'other_ms': {k: acc[k] for k in ('conv1', 'pool1', 'softargmax') if k in acc}}
+    if args.layers:
+        flops = {c.name: c.flops for c in spec.convs}
+        for k, v in acc.items():
+            print(f'{k:28s} {v*1e3:9.1f} us', file=sys.stderr)
+
+    # ---- stand-alone soft-argmax HBM roofline (second half of the BASELINE metric) ----
+    side = spec.feat_side
+    perm = export_permutation(dataset)
+    sam = SoftArgmax(side, j, stride, perm, head_dtype=args.head_dtype)
+    isz = 4 if args.head_dtype == 'f32' else 2
+    heads = []
+    n_rot = max(2, int(np.ceil(300e6 / (n * side * side * 8 * j * isz))))   # rotate > 2x L2 worth of inputs
+    hx = torch.from_numpy(synth_head(min(n, 32), side, j, seed=0)).to(dev)
+    reps_h = int(np.ceil(n / hx.shape[0]))
+    for r in range(n_rot):
+        t = hx.repeat(reps_h, 1, 1, 1)[:n].contiguous().roll(r, 0)
+        heads.append(t.half() if args.head_dtype == 'f16' else t)
+    pout = torch.empty((n, len(perm), 3), dtype=torch.float32, device=dev)
+    for r in range(n_rot):
+        sam(heads[r], pout)
+    torch.cuda.synchronize()
+    iters = 20 * n_rot
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(iters):
+        sam(heads[i % n_rot], pout)
+    s1.record()
+    torch.cuda.synchronize()
+    sam_us = s0.elapsed_time(s1) / iters * 1e3
+    sam_bytes = spec.softargmax_bytes_per_crop(len(perm), isz) * n
+    sam_gbs = sam_bytes / (sam_us * 1e-6) / 1e9
+    roofline_sam = {'kernel': 'softargmax_kernel', 'bound': 'hbm', 'achieved': sam_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': sam_gbs / hbm_peak, 'traffic': None, 'us_per_launch': sam_us, 'bytes_per_launch': sam_bytes,
+                    'note': f'{n_rot} rotating inputs ({n_rot * sam_bytes / 1e6:.0f} MB > L2), back-to-back launches'}
+
+    # ---- CPU baseline beside it (bounded sample; reported, not the target) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = 4
+        rate, dt = cpu_oracle_rate(spec, weights, dataset, sample, cores, repeats=2)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'{sample} crops x 2 passes of config {args.config} ({dt:.2f} s/pass), torch-CPU fp32 oracle port (not TF 1.13)'}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16 operands / f32 accumulate', 'data': 'synthetic',
+        'config': {'workload': f'config {args.config}: {arch} stride_{stride} {j} joints, batch {n}/GPU',
+                   'global_batch': n * world, 'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (2 rotating batches)',
+                   'head_dtype': args.head_dtype, 'gflop_per_crop': spec.flops_per_crop / 1e9,
+                   'tensor_frac_whole_step': spec.flops_per_crop * n / (ms * 1e-3) / 1e12 / tf_sust},
+        'e2e': e2e, 'gpu_launches': model.launch_count(n) * args.steps,
+        'roofline': roofline, 'roofline_softargmax': roofline_sam, 'cpu_baseline': cpu, 'clocks': clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
