@@ -31,45 +31,59 @@ namespace metro {
 
 namespace {
 
+constexpr int kThreads = 256;
+constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
+
 template <int BLOCK_N>
 struct Cfg {
-  static constexpr int kStages = BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 6 : (BLOCK_N <= 160 ? 5 : 4));
   static constexpr int kABytes = kTileM * kTileK * 2;          // 16 KB
   static constexpr int kBBytes = BLOCK_N * kTileK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kAccCols = BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256);  // per stage
+  static constexpr int kAccCols = BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256);  // per accumulator stage
   static constexpr int kTmemCols = 2 * kAccCols;               // power of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * BLOCK_N * 4 + 256 + 1024;
 };
 
-constexpr int kThreads = 256;
+// barrier block layout (uint64 slots): full[8] empty[8] tfull[2] tempty[2] rfull[2], then the TMEM base
+constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarTFull = 2 * kMaxStages, kBarTEmpty = kBarTFull + 2,
+              kBarRFull = kBarTEmpty + 2, kBarCount = kBarRFull + 2;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kDirect>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BLOCK_N>;
-  extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment: required by the 128B swizzle atoms (8 rows x 128 B)
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                                          ~uintptr_t(1023));
+  // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B).  The kernel has no
+  // static shared memory, so the dynamic window starts at the CTA's shared base; verified below.
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("metro: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   unsigned char *tiles = smem;
-  float *s_par = reinterpret_cast<float *>(smem + C::kStages * C::kStageBytes);   // [4][BLOCK_N]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_par + 4 * BLOCK_N);
-  uint64_t *full = bars, *empty = bars + C::kStages;
-  uint64_t *tfull = bars + 2 * C::kStages, *tempty = tfull + 2;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(tempty + 2);
+  float *s_par = reinterpret_cast<float *>(smem + p.off_par);          // [4][BLOCK_N]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+  uint64_t *full = bars + kBarFull, *empty = bars + kBarEmpty;
+  uint64_t *tfull = bars + kBarTFull, *tempty = bars + kBarTEmpty, *rfull = bars + kBarRFull;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + kBarCount);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kb = p.taps * p.cblk0 + p.cblk1;
   const int n_tiles_total = p.m_tiles * p.n_tiles;
+  const int stages = p.stages;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.amap[0]);
     ptx::prefetch_tensormap(&p.bmap);
     if (p.cblk1) ptx::prefetch_tensormap(&p.a2map);
+    if (!kDirect) {
+      if (p.has_out1) ptx::prefetch_tensormap(&p.o1map);
+      if (p.has_out2) ptx::prefetch_tensormap(&p.o2map);
+      if (p.has_res) ptx::prefetch_tensormap(&p.rmap);
+    }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::kStages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); ptx::mbar_init(rfull + i, 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -86,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const int k0 = p.taps * p.cblk0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
         int n0, h0;
@@ -96,7 +111,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           unsigned char *sa = tiles + stage * C::kStageBytes;
           unsigned char *sb = sa + C::kABytes;
           ptx::mbar_arrive_expect_tx(full + stage, C::kStageBytes);
-          const int k0 = p.taps * p.cblk0;
           if (kb < k0) {
             const int tap = kb / p.cblk0, cb = kb - tap * p.cblk0;
             ptx::tma_load_4d(sa, &p.amap[p.tap_map[tap]], full + stage, cb * kTileK, p.tap_dw[tap],
@@ -105,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             ptx::tma_load_4d(sa, &p.a2map, full + stage, (kb - k0) * kTileK, 0, h0, n0);
           }
           ptx::tma_load_2d(sb, &p.bmap, full + stage, kb * kTileK, nt * BLOCK_N);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -131,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::umma_commit(empty + stage);           // frees the smem slot when these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(tfull + acc);               // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; aphase ^= 1; }
@@ -143,98 +157,160 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int et = threadIdx.x - 128;                // 0..127 == accumulator row
     int acc = 0;
     uint32_t aphase = 0;
-    const int hw = p.ho * p.wo;
+    [[maybe_unused]] uint32_t chunk_ctr = 0, rphase0 = 0, rphase1 = 0;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      // stage the per-channel epilogue vectors of this N tile
-      ptx::named_bar_sync(1, 128);
+      const int m0 = mt * kTileM;
+      // per-channel epilogue vectors of this N tile.  Every thread is past the last barrier of the
+      // previous tile, after which nobody reads s_par, so it can be overwritten right away; the
+      // first barrier below publishes it.
+      if constexpr (kDirect) ptx::named_bar_sync(1, 128);   // direct path has no trailing barrier
       for (int i = et; i < BLOCK_N; i += 128) {
         const int c = nt * BLOCK_N + i;
         s_par[i] = p.scale[c];
         s_par[BLOCK_N + i] = p.shift[c];
-        if (p.out2) { s_par[2 * BLOCK_N + i] = p.scale2[c]; s_par[3 * BLOCK_N + i] = p.shift2[c]; }
+        if (p.has_out2) { s_par[2 * BLOCK_N + i] = p.scale2[c]; s_par[3 * BLOCK_N + i] = p.shift2[c]; }
       }
-      ptx::named_bar_sync(1, 128);
-
-      const int m = mt * kTileM + et;
-      const bool valid = m < p.m_total;
-      const __half *res_row = nullptr;
-      if (p.res && valid) {
-        const int n = m / hw, rem = m - n * hw;
-        const int oh = rem / p.wo, ow = rem - oh * p.wo;
-        res_row = p.res + (size_t(n * p.res_h + oh * p.res_stride + p.res_shift) * p.res_w +
-                           ow * p.res_stride + p.res_shift) * p.cout;
-      }
-      ptx::mbar_wait(tfull + acc, aphase);
-      ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * C::kAccCols;
+
+      if constexpr (kDirect) {
+        // ---- fp32 direct-store path (logits head: few columns, masked tail) ----
+        ptx::named_bar_sync(1, 128);
+        const int m = m0 + et;
+        const bool valid = m < p.m_total;
+        ptx::mbar_wait(tfull + acc, aphase);
+        ptx::tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-        const int col0 = nt * BLOCK_N + chunk * 32;
-        if (col0 >= p.cout) break;                   // uniform: padded head columns
-        uint32_t v[32];
-        __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
-        ptx::tmem_ld_32x32(taddr + chunk * 32, v);
-        ptx::tmem_ld_wait();
+        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+          const int col0 = nt * BLOCK_N + chunk * 32;
+          if (col0 >= p.cout) break;                 // uniform: padded head columns
+          uint32_t v[32];
+          __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
+          ptx::tmem_ld_32x32(taddr + chunk * 32, v);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = col0 + 8 * g;
-          if (col >= p.cout) break;                  // uniform (cout is a multiple of 8)
-          float f[8];
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + 8 * g;
+            if (col >= p.cout) break;                // uniform (cout is a multiple of 8)
+            float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int pi = chunk * 32 + 8 * g + i;
-            f[i] = fmaf(__uint_as_float(v[8 * g + i]), s_par[pi], s_par[BLOCK_N + pi]);
+            for (int i = 0; i < 8; ++i) {
+              const int pi = chunk * 32 + 8 * g + i;
+              f[i] = fmaf(__uint_as_float(v[8 * g + i]), s_par[pi], s_par[BLOCK_N + pi]);
+              if (p.relu1) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (valid) {
+              float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out1) + size_t(m) * p.cout + col);
+              dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+              dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+            }
           }
-          if (valid) {
-            if (res_row) {
-              const uint4 r = *reinterpret_cast<const uint4 *>(res_row + col);
-              const __half2 *rh = reinterpret_cast<const __half2 *>(&r);
+        }
+      } else {
+        // ---- fp16 path: TMEM -> registers -> swizzled smem chunk (128 rows x 64 cols) -> TMA store.
+        //      The residual chunk arrives by TMA in the same layout. ----
+        int n0, h0;
+        if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
+        else { n0 = mt * p.nb; h0 = 0; }
+        constexpr int kChunks = BLOCK_N / 64;
+        unsigned char *s_res = smem + p.off_res;
+        if (p.has_res && et == 0) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 rf = __half22float2(rh[i]);
-                f[2 * i] += rf.x;
-                f[2 * i + 1] += rf.y;
-              }
-            }
-            if (p.relu1) {
+          for (int c = 0; c < (kChunks < 2 ? kChunks : 2); ++c) {
+            ptx::mbar_arrive_expect_tx(rfull + c, kChunkBytes);
+            ptx::tma_load_4d(s_res + c * kChunkBytes, &p.rmap, rfull + c, nt * BLOCK_N + c * 64, 0, h0, n0);
+          }
+        }
+        const uint32_t sw = uint32_t(et & 7);
+        const uint32_t row_off = uint32_t(et) * 128;
+        bool waited = false;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++chunk_ctr) {
+          const int ob = (p.obufs == 2) ? int(chunk_ctr & 1) : 0;
+          if (et == 0) {      // the store that last used staging buffer `ob` must have drained it
+            if (p.obufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+          }
+          ptx::named_bar_sync(1, 128);
+          if (!waited) {
+            ptx::mbar_wait(tfull + acc, aphase);
+            ptx::tc_fence_after();
+            waited = true;
+          }
+          unsigned char *so1 = smem + p.off_out1 + ob * kChunkBytes;
+          unsigned char *so2 = smem + p.off_out2 + ob * kChunkBytes;
+          const int rb = c & 1;
+          const unsigned char *sr = s_res + rb * kChunkBytes;
+          if (p.has_res) ptx::mbar_wait(rfull + rb, rb ? rphase1 : rphase0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            const size_t off = size_t(m) * p.cout + col;
-            if (p.out1_f32) {
-              if (p.out1) {
-                float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out1) + off);
-                dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-                dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32(taddr + c * 64 + half * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int j = half * 4 + g;                       // 16-byte chunk within the 128-byte row
+              const uint32_t soff = row_off + ((uint32_t(j) ^ sw) << 4);
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int pi = c * 64 + j * 8 + i;
+                f[i] = fmaf(__uint_as_float(v[8 * g + i]), s_par[pi], s_par[BLOCK_N + pi]);
               }
-            } else {
+              if (p.has_res) {
+                const uint4 r = *reinterpret_cast<const uint4 *>(sr + soff);
+                const __half2 *rh = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 rf = __half22float2(rh[i]);
+                  f[2 * i] += rf.x;
+                  f[2 * i + 1] += rf.y;
+                }
+              }
+              if (p.relu1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
               uint4 o;
               __half2 *oh2 = reinterpret_cast<__half2 *>(&o);
 #pragma unroll
               for (int i = 0; i < 4; ++i) oh2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-              if (p.out1) *reinterpret_cast<uint4 *>(static_cast<__half *>(p.out1) + off) = o;
-              if (p.out2) {
+              if (p.has_out1) *reinterpret_cast<uint4 *>(so1 + soff) = o;
+              if (p.has_out2) {
                 uint4 o2;
                 __half2 *o2h = reinterpret_cast<__half2 *>(&o2);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const int pi = chunk * 32 + 8 * g + 2 * i;
+                  const int pi = c * 64 + j * 8 + 2 * i;
                   const float2 y = __half22float2(oh2[i]);     // the fp16 value the consumer would read
                   const float a = fmaxf(fmaf(y.x, s_par[2 * BLOCK_N + pi], s_par[3 * BLOCK_N + pi]), 0.f);
                   const float b = fmaxf(fmaf(y.y, s_par[2 * BLOCK_N + pi + 1], s_par[3 * BLOCK_N + pi + 1]), 0.f);
                   o2h[i] = __floats2half2_rn(a, b);
                 }
-                *reinterpret_cast<uint4 *>(p.out2 + off) = o2;
+                *reinterpret_cast<uint4 *>(so2 + soff) = o2;
               }
             }
           }
+          ptx::fence_proxy_async();                  // generic-proxy smem writes -> visible to TMA
+          ptx::named_bar_sync(1, 128);
+          if (et == 0) {
+            const int col0 = nt * BLOCK_N + c * 64;
+            if (p.has_out1) ptx::tma_store_2d(&p.o1map, so1, col0, m0);
+            if (p.has_out2) ptx::tma_store_2d(&p.o2map, so2, col0, m0);
+            ptx::bulk_commit();
+            if (p.has_res && c + 2 < kChunks) {      // everyone is done reading s_res[rb]
+              ptx::mbar_arrive_expect_tx(rfull + rb, kChunkBytes);
+              ptx::tma_load_4d(s_res + rb * kChunkBytes, &p.rmap, rfull + rb, col0 + 128, 0, h0, n0);
+            }
+          }
+          if (p.has_res) { if (rb) rphase1 ^= 1; else rphase0 ^= 1; }
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty + acc);
       if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
+    if (!kDirect && et == 0) ptx::bulk_wait<0>();    // smem must outlive the last TMA store
   }
 
   ptx::tc_fence_before();
@@ -262,24 +338,56 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kDirect>
 metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
-  static bool configured = false;
-  if (!configured) {
-    METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::kSmemBytes));
-    configured = true;
+  static int configured = 0;
+  if (configured < L.prm.smem_bytes) {
+    METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemLimit));
+    configured = kSmemLimit;
   }
   const int tiles = L.prm.m_tiles * L.prm.n_tiles;
   if (tiles == 0) return METRO_OK;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  conv_gemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, stream>>>(L.prm);
+  conv_gemm_kernel<BLOCK_N, kDirect><<<grid, kThreads, L.prm.smem_bytes, stream>>>(L.prm);
   METRO_CUDA(cudaGetLastError());
   return METRO_OK;
 }
 
 }  // namespace
+
+metro_status make_tensor_map_4d(CUtensorMap *map, const void *base, const unsigned long long dims_[4],
+                                const unsigned long long strides_[3], const unsigned box_[4]) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+  for (int i = 0; i < 4; ++i) { dims[i] = dims_[i]; box[i] = box_[i]; }
+  for (int i = 0; i < 3; ++i) strides[i] = strides_[i];
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled(4d dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu) -> %d", dims_[0],
+                dims_[1], dims_[2], dims_[3], strides_[0], strides_[1], strides_[2], int(r));
+  return METRO_OK;
+}
+
+metro_status make_out_tensor_map(CUtensorMap *map, const void *base, long long m_rows, int cout) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {cuuint64_t(cout), cuuint64_t(m_rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(cout) * 2};
+  const cuuint32_t box[2] = {64, cuuint32_t(kTileM)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled(output rows=%lld cout=%d) -> %d", m_rows, cout, int(r));
+  return METRO_OK;
+}
 
 metro_status make_act_tensor_map(CUtensorMap *map, const void *base, int n, int h, int w, int c, int sub, int ph,
                                  int pw, int box_w, int box_h, int box_n) {
@@ -316,11 +424,36 @@ metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout
   return METRO_OK;
 }
 
-int conv_gemm_pick_block_n(int cout) {
+int conv_gemm_pick_block_n(int cout, bool direct, bool fancy) {
+  if (direct) return cout <= 160 ? 160 : 256;      // fp32 head: 136 / 152 channels padded to 160
   if (cout <= 64) return 64;
-  if (cout <= 128) return 128;
-  if (cout <= 160) return 160;
+  if (cout <= 128 || fancy) return 128;             // residual / second output need staging room
   return 256;
+}
+
+metro_status conv_gemm_plan_smem(ConvGemmLaunch &L) {
+  ConvGemmParams &p = L.prm;
+  const int stage_bytes = kTileM * kTileK * 2 + L.block_n * kTileK * 2;
+  const int fixed = 4 * L.block_n * 4 + 256;       // epilogue vectors + barrier block
+  int epi = 0;
+  p.obufs = 1;
+  if (!L.direct) {
+    p.obufs = (L.block_n >= 256) ? 1 : 2;           // BLOCK_N 256 keeps 4 pipeline stages instead
+    epi = (p.has_out1 ? p.obufs : 0) * kChunkBytes + (p.has_out2 ? p.obufs : 0) * kChunkBytes +
+          (p.has_res ? 2 : 0) * kChunkBytes;
+  }
+  int stages = (kSmemLimit - fixed - epi) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return fail(METRO_ERR_INTERNAL, "conv_gemm: shared memory plan leaves %d stages", stages);
+  p.stages = stages;
+  int off = stages * stage_bytes;
+  p.off_out1 = off; off += (p.has_out1 && !L.direct ? p.obufs : 0) * kChunkBytes;
+  p.off_out2 = off; off += (p.has_out2 ? p.obufs : 0) * kChunkBytes;
+  p.off_res = off; off += (p.has_res ? 2 : 0) * kChunkBytes;
+  p.off_par = off; off += 4 * L.block_n * 4;
+  p.off_bar = off; off += 256;
+  p.smem_bytes = off;
+  return METRO_OK;
 }
 
 int conv_gemm_cout_pad(int cout, int block_n) { return (cout + block_n - 1) / block_n * block_n; }
@@ -381,10 +514,10 @@ void conv_gemm_pack_weights(const float *w, int k, int cin, int cout, const floa
 
 metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
   switch (L.block_n) {
-    case 64: return launch_t<64>(L, num_sms, stream);
-    case 128: return launch_t<128>(L, num_sms, stream);
-    case 160: return launch_t<160>(L, num_sms, stream);
-    case 256: return launch_t<256>(L, num_sms, stream);
+    case 64: return launch_t<64, false>(L, num_sms, stream);
+    case 128: return launch_t<128, false>(L, num_sms, stream);
+    case 160: return launch_t<160, true>(L, num_sms, stream);
+    case 256: return L.direct ? launch_t<256, true>(L, num_sms, stream) : launch_t<256, false>(L, num_sms, stream);
     default: return fail(METRO_ERR_INTERNAL, "conv_gemm: unsupported BLOCK_N %d", L.block_n);
   }
 }

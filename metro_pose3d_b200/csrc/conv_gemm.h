@@ -13,6 +13,8 @@ namespace metro {
 constexpr int kTileM = 128;     // output pixels per tile (UMMA M)
 constexpr int kTileK = 64;      // fp16 channels per K block = one 128-byte swizzle row
 constexpr int kMaxTaps = 9;
+constexpr int kMaxStages = 8;
+constexpr int kChunkBytes = kTileM * 128;   // one 128-row x 64-column fp16 staging chunk (16 KB)
 
 // Kernel parameters (passed by value as a __grid_constant__; tensor maps must be 64-byte aligned).
 struct alignas(64) ConvGemmParams {
@@ -20,6 +22,9 @@ struct alignas(64) ConvGemmParams {
                          // of a stride-2 conv (entry 0 only for stride 1)
   CUtensorMap a2map;     // optional source 1 (1x1 on the output grid): the projection shortcut
   CUtensorMap bmap;      // packed weights [cout_pad][K_total] fp16, K-major
+  CUtensorMap o1map;     // output 1  [M][cout] fp16 (TMA store), unused on the direct (fp32) path
+  CUtensorMap o2map;     // output 2  [M][cout] fp16
+  CUtensorMap rmap;      // residual, viewed like source 0 on the output grid (sub-sampled / shifted)
   // K loop: taps x cblk0 blocks from source 0, then cblk1 blocks from source 1
   int taps, cblk0, cblk1;
   signed char tap_map[12], tap_dh[12], tap_dw[12];
@@ -28,27 +33,33 @@ struct alignas(64) ConvGemmParams {
   // epilogue: y = acc*scale + shift (+ res) ; relu? ; store y (fp16|fp32) ;
   //           y2 = relu(fp16(y)*scale2 + shift2) -> fp16 (the consumer's pre-activation)
   const float *scale, *shift, *scale2, *shift2;
-  const __half *res;
-  int res_stride, res_shift, res_h, res_w;
-  void *out1;
-  __half *out2;
-  int out1_f32, relu1;
+  void *out1;            // direct path only (fp32)
+  int has_out1, has_out2, has_res, relu1;
+  // shared-memory plan (bytes from the 1024-aligned base)
+  int stages, obufs;
+  int off_out1, off_out2, off_res, off_par, off_bar, smem_bytes;
 };
 
 struct ConvGemmLaunch {
   ConvGemmParams prm;
   int block_n = 128;       // 64 | 128 | 160 | 256
+  bool direct = false;     // fp32 direct-store epilogue (logits head)
   std::string name;
   double flops_per_img = 0;
 };
 
 // Tensor-map helpers (driver entry point resolved at run time; no link-time libcuda dependency).
+metro_status make_tensor_map_4d(CUtensorMap *map, const void *base, const unsigned long long dims[4],
+                                const unsigned long long strides_bytes[3], const unsigned box[4]);
 metro_status make_act_tensor_map(CUtensorMap *map, const void *base, int n, int h, int w, int c,
                                  int sub, int ph, int pw, int box_w, int box_h, int box_n);
 metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout_pad, int k_total, int block_n);
+metro_status make_out_tensor_map(CUtensorMap *map, const void *base, long long m_rows, int cout);
 
-int conv_gemm_pick_block_n(int cout);
+int conv_gemm_pick_block_n(int cout, bool direct, bool fancy);
 int conv_gemm_cout_pad(int cout, int block_n);
+// Lays out shared memory (stage count, staging buffers) once block_n and the has_* flags are set.
+metro_status conv_gemm_plan_smem(ConvGemmLaunch &L);
 // Fills the M-tiling fields for `n` images of an out_side x out_side output.
 metro_status conv_gemm_set_batch(ConvGemmParams &p, int n);
 metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side);

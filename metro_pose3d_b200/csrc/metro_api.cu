@@ -1,5 +1,6 @@
 // C-ABI of libmetro.so (include/metro.h): plan -> device weights + arena + launch list -> infer.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -80,6 +81,13 @@ struct GemmSpec {
   const __half *src = nullptr; int in_side = 0, cin = 0;
   int k = 1, stride = 1, rate = 1, pad_lo = 0, out_side = 0, cout = 0;
   const float *w = nullptr;                 // host HWIO
+  const __half *w_packed_host = nullptr;    // alternative: already packed [cout_pad][K] (root conv)
+  int k_packed = 0;
+  // custom source-0 view (root conv on the space-to-depth image): explicit 4-D tensor map + row taps
+  bool custom_a = false;
+  int c_taps = 0;
+  unsigned long long c_dims[4] = {0, 0, 0, 0}, c_strides[3] = {0, 0, 0};
+  unsigned c_box[4] = {0, 0, 0, 0};
   const __half *src2 = nullptr; int cin2 = 0; const float *w2 = nullptr;
   std::vector<float> scale, shift, scale2, shift2;
   bool relu = false;
@@ -97,27 +105,44 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   L.name = g.name;
   ConvGemmParams &p = L.prm;
   std::memset(&p, 0, sizeof p);
-  L.block_n = conv_gemm_pick_block_n(g.cout);
+  L.direct = g.out1_f32;
+  const bool fancy = (g.out2 != nullptr) || (g.res != nullptr);
+  L.block_n = conv_gemm_pick_block_n(g.cout, L.direct, fancy);
+  if (!L.direct && g.cout % 64 != 0)
+    return fail(METRO_ERR_VALUE, "%s: fp16 outputs need cout %% 64 == 0 (got %d)", g.name.c_str(), g.cout);
+  if (L.direct && (g.out2 || g.res)) return fail(METRO_ERR_VALUE, "%s: fp32 output excludes residual / second output", g.name.c_str());
   const int cout_pad = conv_gemm_cout_pad(g.cout, L.block_n);
   p.cout = g.cout;
   p.n_tiles = cout_pad / L.block_n;
   metro_status st = conv_gemm_geometry(p, g.out_side);
   if (st != METRO_OK) return st;
-  st = conv_gemm_set_taps(p, g.k, g.stride, g.rate, g.pad_lo);
-  if (st != METRO_OK) return st;
-  p.cblk0 = g.cin / kTileK;
-  p.cblk1 = g.cin2 / kTileK;
-  // weights
-  const int K = g.k * g.k * g.cin + g.cin2;
-  std::vector<__half> packed(size_t(cout_pad) * K);
-  conv_gemm_pack_weights(g.w, g.k, g.cin, g.cout, g.w2, g.cin2, cout_pad, packed.data());
+  int K;
+  std::vector<__half> packed;
+  if (g.custom_a) {
+    p.taps = g.c_taps; p.cblk0 = 1; p.cblk1 = 0;
+    for (int t = 0; t < g.c_taps; ++t) { p.tap_map[t] = 0; p.tap_dh[t] = (signed char)t; p.tap_dw[t] = 0; }
+    K = g.k_packed;
+    packed.assign(size_t(cout_pad) * K, __float2half_rn(0.f));
+    std::memcpy(packed.data(), g.w_packed_host, size_t(g.cout) * K * sizeof(__half));
+  } else {
+    st = conv_gemm_set_taps(p, g.k, g.stride, g.rate, g.pad_lo);
+    if (st != METRO_OK) return st;
+    p.cblk0 = g.cin / kTileK;
+    p.cblk1 = g.cin2 / kTileK;
+    K = g.k * g.k * g.cin + g.cin2;
+    packed.resize(size_t(cout_pad) * K);
+    conv_gemm_pack_weights(g.w, g.k, g.cin, g.cout, g.w2, g.cin2, cout_pad, packed.data());
+  }
   __half *d_w = nullptr;
   st = arena.upload(&d_w, packed);
   if (st != METRO_OK) return st;
   st = make_weight_tensor_map(&p.bmap, d_w, cout_pad, K, L.block_n);
   if (st != METRO_OK) return st;
   // activations
-  if (g.stride == 1) {
+  if (g.custom_a) {
+    st = make_tensor_map_4d(&p.amap[0], g.src, g.c_dims, g.c_strides, g.c_box);
+    if (st != METRO_OK) return st;
+  } else if (g.stride == 1) {
     st = make_act_tensor_map(&p.amap[0], g.src, g.n_max, g.in_side, g.in_side, g.cin, 1, 0, 0, p.wo, p.th, p.nb);
     if (st != METRO_OK) return st;
   } else {
@@ -140,10 +165,21 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
     st = arena.upload(&d, g.scale2, cout_pad); if (st != METRO_OK) return st; p.scale2 = d;
     st = arena.upload(&d, g.shift2, cout_pad); if (st != METRO_OK) return st; p.shift2 = d;
   }
-  p.res = g.res; p.res_stride = g.res_stride; p.res_shift = g.res_shift; p.res_h = p.res_w = g.res_side;
-  p.out1 = g.out1; p.out1_f32 = g.out1_f32 ? 1 : 0; p.relu1 = g.relu ? 1 : 0;
-  p.out2 = g.out2;
-  if (g.out1_f32 && g.out2) return fail(METRO_ERR_INTERNAL, "%s: second output needs an fp16 first output", g.name.c_str());
+  p.relu1 = g.relu ? 1 : 0;
+  p.has_out1 = g.out1 ? 1 : 0; p.has_out2 = g.out2 ? 1 : 0; p.has_res = g.res ? 1 : 0;
+  p.out1 = g.out1;
+  const long long m_rows = (long long)g.n_max * g.out_side * g.out_side;
+  if (!L.direct) {
+    if (g.out1 && (st = make_out_tensor_map(&p.o1map, g.out1, m_rows, g.cout)) != METRO_OK) return st;
+    if (g.out2 && (st = make_out_tensor_map(&p.o2map, g.out2, m_rows, g.cout)) != METRO_OK) return st;
+    if (g.res) {
+      // identity shortcut: res[:, shift::stride, shift::stride, :] on the output grid (resnet_v2.py:120-121)
+      st = make_act_tensor_map(&p.rmap, g.res, g.n_max, g.res_side, g.res_side, g.cout, g.res_stride, g.res_shift,
+                               g.res_shift, p.wo, p.th, p.nb);
+      if (st != METRO_OK) return st;
+    }
+  }
+  if ((st = conv_gemm_plan_smem(L)) != METRO_OK) return st;
   L.flops_per_img = 2.0 * g.out_side * g.out_side * double(g.cout) * K;
   conv_gemm_set_batch(p, g.n_max);
   return METRO_OK;
@@ -160,9 +196,11 @@ struct metro_handle {
   std::vector<int32_t> perm;
   NetPlan plan;
   DeviceArena arena;
-  // root
-  float *d_root_w = nullptr, *d_root_b = nullptr, *d_pool_scale = nullptr, *d_pool_shift = nullptr;
-  __half *buf_root = nullptr, *pool_raw = nullptr, *pool_pre = nullptr;
+  // root: space-to-depth pack -> tensor-core conv1 -> pool1 + first pre-activation
+  float *d_pool_scale = nullptr, *d_pool_shift = nullptr;
+  __half *buf_s2d = nullptr, *buf_root = nullptr, *pool_raw = nullptr, *pool_pre = nullptr;
+  int s2d_win = 1, s2d_hp = 0, s2d_wp = 0;
+  ConvGemmLaunch root_gemm;
   std::vector<ConvGemmLaunch> gemms;
   void *buf_head = nullptr;
   SoftargmaxLaunch sam{};
@@ -199,15 +237,54 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     return s;
   };
 
-  // ---- root: conv1 filters as fp16-rounded floats [147][64], bias ----
+  // ---- root: conv1 7x7/2 (pad 3,3) as a 4x4 stride-1 conv on the 2x2 space-to-depth image ----
+  // s2d pixel (h2,w2) holds input pixels (2h2+p, 2w2+q), channel (p*2+q)*3+ch, padded 12 -> 16; the
+  // buffer carries 2 zero rows/cols before and 1 after (131 = 128 + 3).  Input row 2*ho + kh - 3 is
+  // s2d row ho + dh, parity p with kh = 2*dh + p + 3, dh in [-2,1]: four row taps, and the four column
+  // taps x 16 channels are 64 contiguous fp16 = one 128-byte K block, fetched through a tensor map
+  // whose pixel stride (32 B) is smaller than its row extent (overlapping windows; win = 1).  If the
+  // driver rejects that map the windows are materialised instead (win = 4).
   {
-    std::vector<float> w(147 * 64), b(64);
-    for (int i = 0; i < 147 * 64; ++i) w[i] = __half2float(__float2half_rn(blob[pl.root.w_off + i]));
-    for (int i = 0; i < 64; ++i) b[i] = blob[pl.root.b_off + i];
-    if ((st = A.upload(&h.d_root_w, w)) != METRO_OK) return st;
-    if ((st = A.upload(&h.d_root_b, b)) != METRO_OK) return st;
-    if ((st = alloc_half(&h.buf_root, size_t(pl.pool_in) * pl.pool_in * 64)) != METRO_OK) return st;
-    h.debug["conv1"] = {h.buf_root, size_t(pl.pool_in) * pl.pool_in * 64};
+    const int side = pl.pool_in;                      // 128
+    h.s2d_hp = side + 3;
+    std::vector<__half> wp(size_t(64) * 256, __float2half_rn(0.f));
+    const float *w = blob + pl.root.w_off;            // HWIO [7][7][3][64]
+    for (int dhi = 0; dhi < 4; ++dhi)
+      for (int dwi = 0; dwi < 4; ++dwi)
+        for (int pp = 0; pp < 2; ++pp)
+          for (int qq = 0; qq < 2; ++qq) {
+            const int kh = 2 * dhi + pp - 1, kw = 2 * dwi + qq - 1;
+            if (kh < 0 || kw < 0) continue;
+            for (int ch = 0; ch < 3; ++ch)
+              for (int o = 0; o < 64; ++o)
+                wp[size_t(o) * 256 + (dhi * 4 + dwi) * 16 + pp * 6 + qq * 3 + ch] =
+                    __float2half_rn(w[((size_t(kh) * 7 + kw) * 3 + ch) * 64 + o]);
+          }
+    if ((st = alloc_half(&h.buf_root, size_t(side) * side * 64)) != METRO_OK) return st;
+    h.debug["conv1"] = {h.buf_root, size_t(side) * side * 64};
+    GemmSpec g; g.name = "conv1"; g.n_max = N; g.out_side = side; g.cout = 64;
+    g.custom_a = true; g.c_taps = 4; g.w_packed_host = wp.data(); g.k_packed = 256;
+    g.scale.assign(64, 1.0f);
+    g.shift.assign(blob + pl.root.b_off, blob + pl.root.b_off + 64);
+    g.out1 = h.buf_root;
+    const char *force = getenv("METRO_S2D_WIN");
+    for (int win : {1, 4}) {
+      if (force && atoi(force) != win) continue;
+      h.s2d_win = win;
+      h.s2d_wp = (win == 1) ? side + 3 : side;
+      const size_t px_bytes = size_t(win) * 32;
+      void *q = nullptr;
+      if ((st = A.alloc(&q, size_t(N) * h.s2d_hp * h.s2d_wp * px_bytes)) != METRO_OK) return st;
+      h.buf_s2d = static_cast<__half *>(q);
+      g.src = h.buf_s2d;
+      g.c_dims[0] = 64; g.c_dims[1] = side; g.c_dims[2] = h.s2d_hp; g.c_dims[3] = N;
+      g.c_strides[0] = px_bytes; g.c_strides[1] = size_t(h.s2d_wp) * px_bytes;
+      g.c_strides[2] = size_t(h.s2d_hp) * h.s2d_wp * px_bytes;
+      g.c_box[0] = 64; g.c_box[1] = side; g.c_box[2] = 1; g.c_box[3] = 1;
+      st = build_gemm(A, g, h.root_gemm);
+      if (st == METRO_OK) break;
+    }
+    if (st != METRO_OK) return st;
   }
   // ---- sizes of the rotating buffers ----
   size_t raw_elems = size_t(pl.pool_out) * pl.pool_out * 64, r1_elems = 0, r2_elems = 0;
@@ -350,7 +427,10 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
     t->ev.push_back(e); t->names.push_back(name);
   };
   mark("start");
-  if ((st = root_conv_launch(images, u8, h->d_root_w, h->d_root_b, h->buf_root, n, pl.proc_side, pl.pool_in, s)) != METRO_OK) return st;
+  if ((st = s2d_pack_launch(images, u8, h->buf_s2d, n, pl.proc_side, h->s2d_hp, h->s2d_wp, h->s2d_win, s)) != METRO_OK) return st;
+  mark("s2d_pack");
+  conv_gemm_set_batch(h->root_gemm.prm, n);
+  if ((st = conv_gemm_launch(h->root_gemm, h->num_sms, s)) != METRO_OK) return st;
   mark("conv1");
   if ((st = pool_preact_launch(h->buf_root, h->pool_raw, h->pool_pre, h->d_pool_scale, h->d_pool_shift, n, pl.pool_in,
                                pl.pool_out, 64, s)) != METRO_OK) return st;
@@ -570,7 +650,7 @@ metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf,
 
 metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launches) {
   if (!h || !launches) return fail(METRO_ERR_VALUE, "null argument");
-  *launches = n > 0 ? int32_t(h->gemms.size()) + 3 : 0;
+  *launches = n > 0 ? int32_t(h->gemms.size()) + 4 : 0;   // + s2d pack, conv1, pool1, soft-argmax
   return METRO_OK;
 }
 

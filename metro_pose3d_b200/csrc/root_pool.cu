@@ -2,9 +2,9 @@
 // fused with the first unit's pre-activation BN+ReLU.
 //   resnet_v2.py:219-224, resnet_utils.py:124-135 (explicit pad (3,3) then VALID),
 //   resnet_utils.py:177-185 (pad with zeros, not -inf: border maxima are clamped at >= 0).
-// conv1 has Cin = 3 (K = 147): it is computed on the CUDA cores from an fp32 / uint8 NHWC image
-// whose values are rounded to fp16 first (the reference casts the input to FLAGS.dtype,
-// architectures.py:29), fp16-rounded filters, fp32 accumulation, fp16 NHWC output.
+// conv1 has Cin = 3: the image is re-packed (space-to-depth 2x2, fp16) so that the 7x7/2 conv becomes
+// a 4x4 stride-1 conv with 16-channel pixels that the tcgen05 implicit-GEMM kernel (conv_gemm.cu)
+// consumes with K = 4 row taps x 64; see metro_api.cu.
 #include <cuda_fp16.h>
 
 #include "common.h"
@@ -14,70 +14,53 @@ namespace metro {
 
 namespace {
 
-constexpr int kRootTileH = 8, kRootTileW = 32;          // output pixels per CTA (256 threads)
-constexpr int kPatchH = (kRootTileH - 1) * 2 + 7;       // 21
-constexpr int kPatchW = (kRootTileW - 1) * 2 + 7;       // 69
-constexpr int kPatchWPad = kPatchW * 3 + 1;             // floats per patch row (+1: bank spread)
-constexpr int kRootSmem = (147 * 64 + kPatchH * kPatchWPad) * 4;
-
+// Space-to-depth pack: fp32 / uint8 NHWC [n,256,256,3] -> fp16 [n, hp, wp, win*16].
+// thread = one 16-channel group (32 bytes): the 2x2 input pixels of s2d pixel (h2, w2) as
+// [p=0: (q0: r,g,b) (q1: r,g,b)] [p=1: ...] + 4 zeros; values are rounded to fp16 exactly like the
+// reference's cast to FLAGS.dtype (architectures.py:29); the uint8 variant fuses the /255 of
+// improc.py:56-61.  win = 4 additionally replicates each pixel into its 4 sliding-window slots.
 template <bool U8>
-__global__ void __launch_bounds__(256) root_conv_kernel(const void *__restrict__ img, const float *__restrict__ w,
-                                                        const float *__restrict__ bias, __half *__restrict__ out,
-                                                        int in_side, int out_side) {
-  extern __shared__ float sm[];
-  float *s_w = sm;                       // [147][64]  (kh,kw,ci) x cout, already fp16-rounded values
-  float *s_x = sm + 147 * 64;            // [21][69*3 + 1]
-  const int tid = threadIdx.x;
-  const int n = blockIdx.z;
-  const int oh0 = blockIdx.y * kRootTileH, ow0 = blockIdx.x * kRootTileW;
-  for (int i = tid; i < 147 * 64; i += 256) s_w[i] = w[i];
-  const int ih0 = oh0 * 2 - 3, iw0 = ow0 * 2 - 3;
-  for (int i = tid; i < kPatchH * kPatchW * 3; i += 256) {
-    const int r = i / (kPatchW * 3), cc = i - r * (kPatchW * 3);
-    const int ih = ih0 + r, iw = iw0 + cc / 3, ch = cc % 3;
-    float v = 0.f;
-    if (ih >= 0 && ih < in_side && iw >= 0 && iw < in_side) {
-      const size_t idx = ((size_t(n) * in_side + ih) * in_side + iw) * 3 + ch;
-      if (U8) v = float(static_cast<const unsigned char *>(img)[idx]) * (1.0f / 255.0f);
-      else v = static_cast<const float *>(img)[idx];
-      v = __half2float(__float2half_rn(v));
-    }
-    s_x[r * kPatchWPad + cc] = v;
-  }
-  __syncthreads();
-  const int ty = tid / kRootTileW, tx = tid % kRootTileW;
-  float acc[64];
+__global__ void __launch_bounds__(256) s2d_pack_kernel(const void *__restrict__ img, __half *__restrict__ out, int n,
+                                                       int in_side, int hp, int wp, int win) {
+  const size_t total = size_t(n) * hp * wp * win;
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int slot = int(i % win);
+  size_t r = i / win;
+  const int w = int(r % wp); r /= wp;
+  const int h = int(r % hp);
+  const int b = int(r / hp);
+  const int h2 = h - 2, w2 = w + slot - 2;             // s2d coordinates of the source pixel
+  float v[12];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = bias[i];
-#pragma unroll 1
-  for (int kh = 0; kh < 7; ++kh) {
-    const float *xrow = s_x + (ty * 2 + kh) * kPatchWPad + tx * 6;
-#pragma unroll 1
-    for (int t = 0; t < 21; ++t) {       // (kw, ci) flattened: contiguous in the patch row
-      const float x = xrow[t];
-      const float4 *wr = reinterpret_cast<const float4 *>(s_w + (kh * 21 + t) * 64);
+  for (int k = 0; k < 12; ++k) v[k] = 0.f;
+  const int half = in_side / 2;
+  if (h2 >= 0 && h2 < half && w2 >= 0 && w2 < half) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 wv = wr[j];
-        acc[4 * j] = fmaf(x, wv.x, acc[4 * j]);
-        acc[4 * j + 1] = fmaf(x, wv.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(x, wv.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(x, wv.w, acc[4 * j + 3]);
+    for (int p = 0; p < 2; ++p) {
+      const size_t base = ((size_t(b) * in_side + (2 * h2 + p)) * in_side + 2 * w2) * 3;
+      if (U8) {
+        const unsigned char *s = static_cast<const unsigned char *>(img) + base;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[p * 6 + k] = float(s[k]) * (1.0f / 255.0f);
+      } else {
+        const float2 *s = reinterpret_cast<const float2 *>(static_cast<const float *>(img) + base);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float2 t = s[k]; v[p * 6 + 2 * k] = t.x; v[p * 6 + 2 * k + 1] = t.y; }
       }
     }
   }
-  const int oh = oh0 + ty, ow = ow0 + tx;
-  if (oh < out_side && ow < out_side) {
-    uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t(n) * out_side + oh) * out_side + ow) * 64);
+  uint4 o0, o1;
+  __half2 *a = reinterpret_cast<__half2 *>(&o0), *c = reinterpret_cast<__half2 *>(&o1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint4 o;
-      __half2 *oh2 = reinterpret_cast<__half2 *>(&o);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) oh2[i] = __floats2half2_rn(acc[8 * j + 2 * i], acc[8 * j + 2 * i + 1]);
-      dst[j] = o;
-    }
-  }
+  for (int k = 0; k < 4; ++k) a[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+  c[0] = __floats2half2_rn(v[8], v[9]);
+  c[1] = __floats2half2_rn(v[10], v[11]);
+  c[2] = __floats2half2_rn(0.f, 0.f);
+  c[3] = c[2];
+  uint4 *dst = reinterpret_cast<uint4 *>(out + i * 16);
+  dst[0] = o0;
+  dst[1] = o1;
 }
 
 // pool1 + first pre-activation.  thread = 8 channels of one output pixel.
@@ -127,18 +110,13 @@ __global__ void __launch_bounds__(256) pool_preact_kernel(const __half *__restri
 
 }  // namespace
 
-metro_status root_conv_launch(const void *img, bool u8, const float *w, const float *bias, __half *out, int n,
-                              int in_side, int out_side, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    METRO_CUDA(cudaFuncSetAttribute(root_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRootSmem));
-    METRO_CUDA(cudaFuncSetAttribute(root_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRootSmem));
-    configured = true;
-  }
+metro_status s2d_pack_launch(const void *img, bool u8, __half *out, int n, int in_side, int hp, int wp, int win,
+                             cudaStream_t stream) {
   if (n == 0) return METRO_OK;
-  const dim3 grid((out_side + kRootTileW - 1) / kRootTileW, (out_side + kRootTileH - 1) / kRootTileH, n);
-  if (u8) root_conv_kernel<true><<<grid, 256, kRootSmem, stream>>>(img, w, bias, out, in_side, out_side);
-  else root_conv_kernel<false><<<grid, 256, kRootSmem, stream>>>(img, w, bias, out, in_side, out_side);
+  const size_t total = size_t(n) * hp * wp * win;
+  const unsigned blocks = unsigned((total + 255) / 256);
+  if (u8) s2d_pack_kernel<true><<<blocks, 256, 0, stream>>>(img, out, n, in_side, hp, wp, win);
+  else s2d_pack_kernel<false><<<blocks, 256, 0, stream>>>(img, out, n, in_side, hp, wp, win);
   METRO_CUDA(cudaGetLastError());
   return METRO_OK;
 }
