@@ -43,9 +43,9 @@ struct Cfg {
   static constexpr int kTmemCols = 2 * kAccCols;               // power of two >= 32
 };
 
-// barrier block layout (uint64 slots): full[8] empty[8] tfull[2] tempty[2] rfull[2], then the TMEM base
+// barrier block layout (uint64 slots): full[8] empty[8] tfull[2] tempty[2], then the TMEM base
 constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarTFull = 2 * kMaxStages, kBarTEmpty = kBarTFull + 2,
-              kBarRFull = kBarTEmpty + 2, kBarCount = kBarRFull + 2;
+              kBarCount = kBarTEmpty + 2;
 
 template <int BLOCK_N, bool kDirect>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -61,11 +61,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   float *s_par = reinterpret_cast<float *>(smem + p.off_par);          // [4][BLOCK_N]
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
   uint64_t *full = bars + kBarFull, *empty = bars + kBarEmpty;
-  uint64_t *tfull = bars + kBarTFull, *tempty = bars + kBarTEmpty, *rfull = bars + kBarRFull;
+  uint64_t *tfull = bars + kBarTFull, *tempty = bars + kBarTEmpty;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + kBarCount);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_kb = p.taps * p.cblk0 + p.cblk1;
+  // K blocks per tile: taps x cblk0 from source 0, then source 1: all cblk1 blocks (projection
+  // shortcut) or, for the identity shortcut (diag2), only the BLOCK_N/64 blocks whose identity
+  // weights hit this N tile.
+  const int k0 = p.taps * p.cblk0;
   const int n_tiles_total = p.m_tiles * p.n_tiles;
   const int stages = p.stages;
 
@@ -76,14 +79,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (!kDirect) {
       if (p.has_out1) ptx::prefetch_tensormap(&p.o1map);
       if (p.has_out2) ptx::prefetch_tensormap(&p.o2map);
-      if (p.has_res) ptx::prefetch_tensormap(&p.rmap);
     }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); ptx::mbar_init(rfull + i, 1);
-    }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -100,12 +100,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int k0 = p.taps * p.cblk0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
         int n0, h0;
         if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
         else { n0 = mt * p.nb; h0 = 0; }
+        const int cb2_0 = p.diag2 ? nt * (BLOCK_N / 64) : 0;
+        const int n_kb = k0 + (p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1);
         for (int kb = 0; kb < n_kb; ++kb) {
           ptx::mbar_wait(empty + stage, phase ^ 1);
           unsigned char *sa = tiles + stage * C::kStageBytes;
@@ -115,10 +116,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int tap = kb / p.cblk0, cb = kb - tap * p.cblk0;
             ptx::tma_load_4d(sa, &p.amap[p.tap_map[tap]], full + stage, cb * kTileK, p.tap_dw[tap],
                              h0 + p.tap_dh[tap], n0);
+            ptx::tma_load_2d(sb, &p.bmap, full + stage, kb * kTileK, nt * BLOCK_N);
           } else {
-            ptx::tma_load_4d(sa, &p.a2map, full + stage, (kb - k0) * kTileK, 0, h0, n0);
+            const int cb = cb2_0 + kb - k0;
+            ptx::tma_load_4d(sa, &p.a2map, full + stage, cb * kTileK, 0, h0, n0);
+            ptx::tma_load_2d(sb, &p.bmap, full + stage, (k0 + cb) * kTileK, nt * BLOCK_N);
           }
-          ptx::tma_load_2d(sb, &p.bmap, full + stage, kb * kTileK, nt * BLOCK_N);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -130,6 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       int stage = 0, acc = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int n_kb = k0 + (p.diag2 ? min(BLOCK_N / 64, p.cblk1 - nt * (BLOCK_N / 64)) : p.cblk1);
         ptx::mbar_wait(tempty + acc, aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int et = threadIdx.x - 128;                // 0..127 == accumulator row
     int acc = 0;
     uint32_t aphase = 0;
-    [[maybe_unused]] uint32_t chunk_ctr = 0, rphase0 = 0, rphase1 = 0;
+    [[maybe_unused]] uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const int m0 = mt * kTileM;
@@ -200,27 +205,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               if (p.relu1) f[i] = fmaxf(f[i], 0.f);
             }
             if (valid) {
-              float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out1) + size_t(m) * p.cout + col);
-              dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-              dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+              const size_t off = size_t(m) * p.cout + col;
+              if (p.out1_f32) {
+                float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out1) + off);
+                dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                uint4 o;
+                __half2 *oh2 = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) oh2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                *reinterpret_cast<uint4 *>(static_cast<__half *>(p.out1) + off) = o;
+              }
             }
           }
         }
       } else {
         // ---- fp16 path: TMEM -> registers -> swizzled smem chunk (128 rows x 64 cols) -> TMA store.
-        //      The residual chunk arrives by TMA in the same layout. ----
-        int n0, h0;
-        if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
-        else { n0 = mt * p.nb; h0 = 0; }
+        //      (The identity-shortcut residual is not an epilogue operand: it is accumulated by the
+        //      tensor core as extra K blocks against identity weights, see the producer.) ----
         constexpr int kChunks = BLOCK_N / 64;
-        unsigned char *s_res = smem + p.off_res;
-        if (p.has_res && et == 0) {
-#pragma unroll
-          for (int c = 0; c < (kChunks < 2 ? kChunks : 2); ++c) {
-            ptx::mbar_arrive_expect_tx(rfull + c, kChunkBytes);
-            ptx::tma_load_4d(s_res + c * kChunkBytes, &p.rmap, rfull + c, nt * BLOCK_N + c * 64, 0, h0, n0);
-          }
-        }
         const uint32_t sw = uint32_t(et & 7);
         const uint32_t row_off = uint32_t(et) * 128;
         bool waited = false;
@@ -238,9 +242,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           unsigned char *so1 = smem + p.off_out1 + ob * kChunkBytes;
           unsigned char *so2 = smem + p.off_out2 + ob * kChunkBytes;
-          const int rb = c & 1;
-          const unsigned char *sr = s_res + rb * kChunkBytes;
-          if (p.has_res) ptx::mbar_wait(rfull + rb, rb ? rphase1 : rphase0);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
@@ -256,16 +257,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               for (int i = 0; i < 8; ++i) {
                 const int pi = c * 64 + j * 8 + i;
                 f[i] = fmaf(__uint_as_float(v[8 * g + i]), s_par[pi], s_par[BLOCK_N + pi]);
-              }
-              if (p.has_res) {
-                const uint4 r = *reinterpret_cast<const uint4 *>(sr + soff);
-                const __half2 *rh = reinterpret_cast<const __half2 *>(&r);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 rf = __half22float2(rh[i]);
-                  f[2 * i] += rf.x;
-                  f[2 * i + 1] += rf.y;
-                }
               }
               if (p.relu1) {
 #pragma unroll
@@ -298,12 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (p.has_out1) ptx::tma_store_2d(&p.o1map, so1, col0, m0);
             if (p.has_out2) ptx::tma_store_2d(&p.o2map, so2, col0, m0);
             ptx::bulk_commit();
-            if (p.has_res && c + 2 < kChunks) {      // everyone is done reading s_res[rb]
-              ptx::mbar_arrive_expect_tx(rfull + rb, kChunkBytes);
-              ptx::tma_load_4d(s_res + rb * kChunkBytes, &p.rmap, rfull + rb, col0 + 128, 0, h0, n0);
-            }
           }
-          if (p.has_res) { if (rb) rphase1 ^= 1; else rphase0 ^= 1; }
         }
       }
       ptx::tc_fence_before();
@@ -424,32 +410,29 @@ metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout
   return METRO_OK;
 }
 
-int conv_gemm_pick_block_n(int cout, bool direct, bool fancy) {
-  if (direct) return cout <= 160 ? 160 : 256;      // fp32 head: 136 / 152 channels padded to 160
+int conv_gemm_pick_block_n(int cout, bool direct) {
+  if (direct) return cout <= 160 ? 160 : 256;      // logits head: 136 / 152 channels padded to 160
   if (cout <= 64) return 64;
-  if (cout <= 128 || fancy) return 128;             // residual / second output need staging room
+  if (cout <= 128) return 128;
   return 256;
 }
 
-metro_status conv_gemm_plan_smem(ConvGemmLaunch &L) {
+metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks) {
   ConvGemmParams &p = L.prm;
   const int stage_bytes = kTileM * kTileK * 2 + L.block_n * kTileK * 2;
   const int fixed = 4 * L.block_n * 4 + 256;       // epilogue vectors + barrier block
-  int epi = 0;
-  p.obufs = 1;
-  if (!L.direct) {
-    p.obufs = (L.block_n >= 256) ? 1 : 2;           // BLOCK_N 256 keeps 4 pipeline stages instead
-    epi = (p.has_out1 ? p.obufs : 0) * kChunkBytes + (p.has_out2 ? p.obufs : 0) * kChunkBytes +
-          (p.has_res ? 2 : 0) * kChunkBytes;
-  }
-  int stages = (kSmemLimit - fixed - epi) / stage_bytes;
+  const int n_out = L.direct ? 0 : (p.has_out1 ? 1 : 0) + (p.has_out2 ? 1 : 0);
+  auto stages_for = [&](int obufs) { return (kSmemLimit - fixed - n_out * obufs * kChunkBytes) / stage_bytes; };
+  // double-buffered staging unless a long K loop would rather have one more pipeline stage
+  p.obufs = 2;
+  if (n_out && k_blocks >= 8 && stages_for(2) < 4 && stages_for(1) >= 4) p.obufs = 1;
+  int stages = stages_for(p.obufs);
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(METRO_ERR_INTERNAL, "conv_gemm: shared memory plan leaves %d stages", stages);
   p.stages = stages;
   int off = stages * stage_bytes;
   p.off_out1 = off; off += (p.has_out1 && !L.direct ? p.obufs : 0) * kChunkBytes;
   p.off_out2 = off; off += (p.has_out2 ? p.obufs : 0) * kChunkBytes;
-  p.off_res = off; off += (p.has_res ? 2 : 0) * kChunkBytes;
   p.off_par = off; off += 4 * L.block_n * 4;
   p.off_bar = off; off += 256;
   p.smem_bytes = off;
@@ -499,6 +482,7 @@ metro_status conv_gemm_set_taps(ConvGemmParams &p, int k, int stride, int rate, 
 
 void conv_gemm_pack_weights(const float *w, int k, int cin, int cout, const float *w2, int cin2, int cout_pad,
                             __half *dst) {
+  // w2 == nullptr with cin2 > 0: identity block (the shortcut is the raw input itself)
   const size_t K = size_t(k) * k * cin + cin2;
   std::memset(dst, 0, size_t(cout_pad) * K * sizeof(__half));
   for (int t = 0; t < k * k; ++t)
@@ -507,6 +491,10 @@ void conv_gemm_pack_weights(const float *w, int k, int cin, int cout, const floa
       for (int o = 0; o < cout; ++o) dst[size_t(o) * K + size_t(t) * cin + c] = __float2half_rn(src[o]);
     }
   for (int c = 0; c < cin2; ++c) {
+    if (!w2) {
+      if (c < cout) dst[size_t(c) * K + size_t(k) * k * cin + c] = __float2half_rn(1.0f);
+      continue;
+    }
     const float *src = w2 + size_t(c) * cout;
     for (int o = 0; o < cout; ++o) dst[size_t(o) * K + size_t(k) * k * cin + c] = __float2half_rn(src[o]);
   }

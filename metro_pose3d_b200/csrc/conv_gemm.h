@@ -20,30 +20,31 @@ constexpr int kChunkBytes = kTileM * 128;   // one 128-row x 64-column fp16 stag
 struct alignas(64) ConvGemmParams {
   CUtensorMap amap[4];   // source 0, NHWC fp16, viewed as [C, W', H', N]; 4 = (row,col) parity views
                          // of a stride-2 conv (entry 0 only for stride 1)
-  CUtensorMap a2map;     // optional source 1 (1x1 on the output grid): the projection shortcut
+  CUtensorMap a2map;     // optional source 1 (1x1 on the output grid): the projection shortcut's input, or
+                         // the identity shortcut's raw tensor (sub-sampled / shifted view) with diag2 = 1
   CUtensorMap bmap;      // packed weights [cout_pad][K_total] fp16, K-major
   CUtensorMap o1map;     // output 1  [M][cout] fp16 (TMA store), unused on the direct (fp32) path
   CUtensorMap o2map;     // output 2  [M][cout] fp16
-  CUtensorMap rmap;      // residual, viewed like source 0 on the output grid (sub-sampled / shifted)
   // K loop: taps x cblk0 blocks from source 0, then cblk1 blocks from source 1
-  int taps, cblk0, cblk1;
+  int taps, cblk0, cblk1, diag2;
   signed char tap_map[12], tap_dh[12], tap_dw[12];
   // M tiling: a tile is 128 consecutive output pixels = th full rows of nb images
   int m_total, wo, ho, th, nb, tiles_per_img, m_tiles, n_tiles, cout;
   // epilogue: y = acc*scale + shift (+ res) ; relu? ; store y (fp16|fp32) ;
   //           y2 = relu(fp16(y)*scale2 + shift2) -> fp16 (the consumer's pre-activation)
   const float *scale, *shift, *scale2, *shift2;
-  void *out1;            // direct path only (fp32)
-  int has_out1, has_out2, has_res, relu1;
+  void *out1;            // direct-store path only (logits head)
+  int out1_f32;
+  int has_out1, has_out2, relu1;
   // shared-memory plan (bytes from the 1024-aligned base)
   int stages, obufs;
-  int off_out1, off_out2, off_res, off_par, off_bar, smem_bytes;
+  int off_out1, off_out2, off_par, off_bar, smem_bytes;
 };
 
 struct ConvGemmLaunch {
   ConvGemmParams prm;
   int block_n = 128;       // 64 | 128 | 160 | 256
-  bool direct = false;     // fp32 direct-store epilogue (logits head)
+  bool direct = false;     // direct-store epilogue (logits head: cout not a multiple of 64)
   std::string name;
   double flops_per_img = 0;
 };
@@ -56,10 +57,10 @@ metro_status make_act_tensor_map(CUtensorMap *map, const void *base, int n, int 
 metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout_pad, int k_total, int block_n);
 metro_status make_out_tensor_map(CUtensorMap *map, const void *base, long long m_rows, int cout);
 
-int conv_gemm_pick_block_n(int cout, bool direct, bool fancy);
+int conv_gemm_pick_block_n(int cout, bool direct);
 int conv_gemm_cout_pad(int cout, int block_n);
 // Lays out shared memory (stage count, staging buffers) once block_n and the has_* flags are set.
-metro_status conv_gemm_plan_smem(ConvGemmLaunch &L);
+metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks);
 // Fills the M-tiling fields for `n` images of an out_side x out_side output.
 metro_status conv_gemm_set_batch(ConvGemmParams &p, int n);
 metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side);

@@ -105,12 +105,15 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   L.name = g.name;
   ConvGemmParams &p = L.prm;
   std::memset(&p, 0, sizeof p);
-  L.direct = g.out1_f32;
-  const bool fancy = (g.out2 != nullptr) || (g.res != nullptr);
-  L.block_n = conv_gemm_pick_block_n(g.cout, L.direct, fancy);
-  if (!L.direct && g.cout % 64 != 0)
-    return fail(METRO_ERR_VALUE, "%s: fp16 outputs need cout %% 64 == 0 (got %d)", g.name.c_str(), g.cout);
-  if (L.direct && (g.out2 || g.res)) return fail(METRO_ERR_VALUE, "%s: fp32 output excludes residual / second output", g.name.c_str());
+  L.direct = g.out1_f32 || (g.cout % 64 != 0);   // the logits head (136 / 152 channels, fp32 or fp16)
+  L.block_n = conv_gemm_pick_block_n(g.cout, L.direct);
+  if (L.direct && (g.out2 || g.res)) return fail(METRO_ERR_VALUE, "%s: this output shape excludes a residual / second output", g.name.c_str());
+  if (g.res && g.cin2) return fail(METRO_ERR_VALUE, "%s: identity and projection shortcuts are exclusive", g.name.c_str());
+  if (g.res) {
+    for (float sc : g.scale)
+      if (sc != 1.0f) return fail(METRO_ERR_VALUE, "%s: the residual is accumulated before the scale; scale must be 1", g.name.c_str());
+  }
+  const int res_c = g.res ? g.cout : 0;           // identity shortcut rides the K loop as identity weights
   const int cout_pad = conv_gemm_cout_pad(g.cout, L.block_n);
   p.cout = g.cout;
   p.n_tiles = cout_pad / L.block_n;
@@ -128,10 +131,11 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
     st = conv_gemm_set_taps(p, g.k, g.stride, g.rate, g.pad_lo);
     if (st != METRO_OK) return st;
     p.cblk0 = g.cin / kTileK;
-    p.cblk1 = g.cin2 / kTileK;
-    K = g.k * g.k * g.cin + g.cin2;
+    p.cblk1 = (g.cin2 + res_c) / kTileK;
+    p.diag2 = g.res ? 1 : 0;
+    K = g.k * g.k * g.cin + g.cin2 + res_c;
     packed.resize(size_t(cout_pad) * K);
-    conv_gemm_pack_weights(g.w, g.k, g.cin, g.cout, g.w2, g.cin2, cout_pad, packed.data());
+    conv_gemm_pack_weights(g.w, g.k, g.cin, g.cout, g.res ? nullptr : g.w2, g.cin2 + res_c, cout_pad, packed.data());
   }
   __half *d_w = nullptr;
   st = arena.upload(&d_w, packed);
@@ -156,6 +160,11 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   if (g.cin2) {
     st = make_act_tensor_map(&p.a2map, g.src2, g.n_max, g.out_side, g.out_side, g.cin2, 1, 0, 0, p.wo, p.th, p.nb);
     if (st != METRO_OK) return st;
+  } else if (g.res) {
+    // identity shortcut: res[:, shift::stride, shift::stride, :] on the output grid (resnet_v2.py:120-121)
+    st = make_act_tensor_map(&p.a2map, g.res, g.n_max, g.res_side, g.res_side, g.cout, g.res_stride, g.res_shift,
+                             g.res_shift, p.wo, p.th, p.nb);
+    if (st != METRO_OK) return st;
   }
   // epilogue vectors (padded to cout_pad so the kernel never reads out of range)
   float *d = nullptr;
@@ -166,20 +175,17 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
     st = arena.upload(&d, g.shift2, cout_pad); if (st != METRO_OK) return st; p.shift2 = d;
   }
   p.relu1 = g.relu ? 1 : 0;
-  p.has_out1 = g.out1 ? 1 : 0; p.has_out2 = g.out2 ? 1 : 0; p.has_res = g.res ? 1 : 0;
-  p.out1 = g.out1;
+  p.has_out1 = g.out1 ? 1 : 0; p.has_out2 = g.out2 ? 1 : 0;
+  p.out1 = g.out1; p.out1_f32 = g.out1_f32 ? 1 : 0;
   const long long m_rows = (long long)g.n_max * g.out_side * g.out_side;
   if (!L.direct) {
     if (g.out1 && (st = make_out_tensor_map(&p.o1map, g.out1, m_rows, g.cout)) != METRO_OK) return st;
     if (g.out2 && (st = make_out_tensor_map(&p.o2map, g.out2, m_rows, g.cout)) != METRO_OK) return st;
-    if (g.res) {
-      // identity shortcut: res[:, shift::stride, shift::stride, :] on the output grid (resnet_v2.py:120-121)
-      st = make_act_tensor_map(&p.rmap, g.res, g.n_max, g.res_side, g.res_side, g.cout, g.res_stride, g.res_shift,
-                               g.res_shift, p.wo, p.th, p.nb);
-      if (st != METRO_OK) return st;
-    }
   }
-  if ((st = conv_gemm_plan_smem(L)) != METRO_OK) return st;
+  {
+    const int kb_tile = p.taps * p.cblk0 + (p.diag2 ? L.block_n / 64 : p.cblk1);
+    if ((st = conv_gemm_plan_smem(L, kb_tile)) != METRO_OK) return st;
+  }
   L.flops_per_img = 2.0 * g.out_side * g.out_side * double(g.cout) * K;
   conv_gemm_set_batch(p, g.n_max);
   return METRO_OK;
