@@ -26,13 +26,13 @@ constexpr int kMaxJointsOut = 64;
 struct SoftargmaxLaunch {
   const void *head;
   float *out;
-  double *partials;        // [n][splits][J][5] : M, S, Sx, Sy, Sz
+  double *partials;        // [n][splits][J][5] : K (integer base-2 exponent), S, Sx, Sy, Sz
   unsigned int *counters;  // [n], zero between launches
   int n, H, W, J, D, C;
   int n_out, root;
   int perm[kMaxJointsOut];
   double mul_x, mul_y, mul_z;  // mm per unit of (Sx/S), (Sy/S), (Sz/S)
-  int splits, lanes, slots, ppc;
+  int splits, lanes, slots, ppc, rpt, off_ch;
   int head_f16;
 };
 metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLaunch &L);

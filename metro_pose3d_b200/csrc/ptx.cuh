@@ -81,6 +81,14 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const void *desc, ui
       : "memory");
 }
 
+// contiguous global -> smem bulk copy (UBLKCP); src, dst and size must be multiples of 16 bytes
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // smem -> global tile store (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const void *desc, const void *smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

@@ -9,11 +9,16 @@ from oracle.metro_oracle import OracleNet
 
 pytestmark = pytest.mark.gpu
 
-# End-to-end tolerance against the oracle that rounds to fp16 at the same points ('half' mode): the
-# remaining difference is fp32-vs-exact accumulation flipping individual fp16 roundings.  The strict
-# 1e-3 mm bound applies to the decode on identical logits (tests/test_softargmax_gpu.py).
-E2E_TOL_MM = 0.5
+# End-to-end tolerances.  The reference computes the backbone in float16 (src/options.py:73), so its
+# output is only defined up to the summation order of its fp16 convolutions: the oracle that rounds to
+# fp16 at the same storage points ('half' mode) and the CUDA path differ wherever fp32-vs-exact
+# accumulation flips an individual fp16 rounding, and those flips random-walk through ~50 layers.  The
+# e2e bound is therefore stated against the fp16 noise floor itself: |cuda - fp64| and |cuda - half|
+# must stay within 1.5x (+0.25 mm) of |half - fp64|, the distance between two legitimate evaluations
+# of the same fp16 graph.  The strict 1e-3 mm bound of BASELINE.json applies to the decode on
+# identical logits (checked below on the path's own head tensor and in tests/test_softargmax_gpu.py).
 LAYER_REL = 2e-3
+DECODE_TOL_MM = 1e-3
 
 
 def _rel(a, b):
@@ -48,8 +53,16 @@ def test_layerwise_and_end_to_end(arch, stride, ds):
     report.append(('head', _rel(got_head, head)))
     worst = max(report, key=lambda r: r[1])
     assert worst[1] < LAYER_REL, f'worst layer {worst}; first bad: {[r for r in report if r[1] >= LAYER_REL][:3]}'
-    err = np.abs(poses - ref).max()
-    assert err < E2E_TOL_MM, f'end-to-end max |err| = {err:.4f} mm'
+    # strict: the decode of the path's own head tensor
+    strict = np.abs(poses - ora.decode(got_head)).max()
+    assert strict < DECODE_TOL_MM, f'decode on identical logits: max |err| = {strict:.3e} mm'
+    # end to end against the fp16 noise floor
+    p64 = OracleNet(spec, w, perm, 'fp64')(img)
+    noise = np.abs(ref - p64).max()
+    bound = 1.5 * noise + 0.25
+    err_half, err64 = np.abs(poses - ref).max(), np.abs(poses - p64).max()
+    assert err_half < bound and err64 < bound, \
+        f'end-to-end: |cuda-half| {err_half:.3f} mm, |cuda-fp64| {err64:.3f} mm, fp16 noise floor {noise:.3f} mm'
     assert poses.shape == (n, 17, 3) and np.all(poses[:, 0] == 0)
     assert edges.shape == (16, 2) and names[0] == 'pelv'
 

@@ -27,33 +27,40 @@ def stage_sam():
             got = SoftArgmax(side, j, stride, perm, head_dtype=dt)(t).cpu().numpy()
             ref = decode_ref(xx, j, stride, perm)
             print(f'sam side={side} J={j} {dt}: max err {np.abs(got-ref).max():.3e} mm', flush=True)
-    # timing sweep, config B and D/E-like shapes, rotating inputs > L2
+    # timing sweep, config B and D/E-like shapes, rotating inputs > L2; launches replayed from a CUDA graph
+    # so the figure is device time per launch, not Python/ctypes call overhead
     for side, stride, j, n in [(16, 16, 17, 256), (16, 16, 19, 256), (32, 8, 19, 64), (64, 4, 19, 128)]:
         perm = list(range(j))
         base = torch.from_numpy(synth_head(8, side, j, seed=0)).cuda()
         for dt in ('f32', 'f16'):
             isz = 4 if dt == 'f32' else 2
             nbytes = n * side * side * 8 * j * isz
-            nrot = max(2, int(np.ceil(300e6 / nbytes)))
+            nrot = max(2, int(np.ceil(400e6 / nbytes)))
             heads = []
             for r in range(nrot):
                 h = base.repeat((n + 7) // 8, 1, 1, 1)[:n].roll(r, 0).contiguous()
                 heads.append(h.half() if dt == 'f16' else h)
-            for splits, lanes in [(0, 0), (0, 4), (0, 6), (0, 8), (0, 16), (0, 20)]:
+            P = side * side
+            for lanes, splits in [(0, 0), (8, max(1, P // 128)), (8, max(1, P // 64)), (8, max(1, P // 32)), (8, max(1, P // 16)),
+                                  (4, max(1, P // 64)), (4, max(1, P // 32)), (4, max(1, P // 16)), (9, max(1, P // 72))]:
                 try:
                     op = SoftArgmax(side, j, stride, perm, head_dtype=dt, splits=splits, lanes=lanes)
                     out = torch.empty((n, j, 3), device='cuda')
                     for r in range(nrot): op(heads[r], out)
                     torch.cuda.synchronize()
+                    it = 4 * nrot
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for i in range(it): op(heads[i % nrot], out)
+                    g.replay(); torch.cuda.synchronize()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    it = 10 * nrot
                     e0.record()
-                    for i in range(it): op(heads[i % nrot], out)
+                    for _ in range(5): g.replay()
                     e1.record(); torch.cuda.synchronize()
-                    us = e0.elapsed_time(e1) / it * 1e3
-                    print(f'sam-time side={side} J={j} n={n} {dt} lanes={lanes}: {us:8.2f} us  {nbytes/us/1e3:8.1f} GB/s', flush=True)
+                    us = e0.elapsed_time(e1) / (5 * it) * 1e3
+                    print(f'sam-time side={side} J={j} n={n} {dt} lanes={lanes} splits={splits}: {us:8.2f} us  {nbytes/us/1e3:8.1f} GB/s', flush=True)
                 except Exception as e:
-                    print(f'sam-time side={side} J={j} {dt} lanes={lanes}: ERROR {e}', flush=True)
+                    print(f'sam-time side={side} J={j} {dt} lanes={lanes} splits={splits}: ERROR {e}', flush=True)
 
 
 def _conv_case(n, side, cin, cout, k, stride, rate, pad_lo, verbose=True):
