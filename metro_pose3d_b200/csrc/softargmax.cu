@@ -11,18 +11,25 @@
 // (channel c = d*J + j) is read exactly once with 16-byte coalesced loads and
 //   out[n,jo,:] = (E_j[w]/(W-1), E_j[h]/(H-1), E_j[d]/(D-1)) - same for the root, times mm scales.
 //
-// Layout of work: a CTA owns `ppc` consecutive pixels of one crop = ONE contiguous byte range of the
-// head tensor, which a single elected thread fetches with one bulk asynchronous copy (cp.async.bulk,
-// the TMA engine) into shared memory; several CTAs are resident per SM, so tens of KB per SM are in
-// flight without costing a register, and one CTA's reduction tail overlaps the others' copies.
-// thread = (pixel lane, 16-byte channel slot): shared-memory reads are conflict-free 16-byte words.
+// Layout of work: the head tensor of one crop is a contiguous byte range; it is cut into tiles of
+// whole heatmap rows (~35 KB).  A CTA is PERSISTENT over work items (item = one crop, or one of
+// `splits` row ranges of a large crop) and streams each item tile by tile through a 2-stage shared
+// memory ring: an elected thread issues bulk asynchronous copies (cp.async.bulk, the TMA engine) one
+// ring ahead -- also across item boundaries -- so the HBM stream never waits for arithmetic, and with
+// 2-3 CTAs per SM ~150 KB per SM are in flight without costing a register.
+// thread = (16-byte channel slot, pixel lane); a thread walks pixels lane, lane+LANES, ... of a tile,
+// so shared-memory reads are conflict-free 16-byte words, and it keeps its channels' running sums in
+// registers for the whole item: the only cross-thread work (lane shuffle, depth merge, output) happens
+// once per item, not per tile.  The kernel is close to instruction bound at HBM speed (one exp per
+// element), so the inner loop is 2-wide packed fp32 (FFMA2/FADD2) and carries no address arithmetic.
 //
-// Numerics: exp(x - max) is evaluated in base 2 against an INTEGER exponent k >= max * log2(e) taken
-// per (thread, channel).  Because every partial record carries an integer exponent, all merges (pixel
-// lanes -> channel -> depth -> joint -> CTA splits) re-scale by exact powers of two: there is no
-// transcendental and no rounding in the merge weights, and the merged sums are carried in fp64.  The
-// only fp32 roundings are ex2.approx per element and the short per-thread sums, which keeps the result
-// within 1e-3 mm of the float64 oracle.
+// Numerics: exp(x - max) is evaluated in base 2 against an INTEGER exponent k >= max * log2(e) kept
+// per (thread, channel) and raised -- with an exact power-of-two re-scale of the running sums -- when a
+// later tile holds a larger value.  Per-tile partial sums (<= 32 terms, two-level) are fp32; running
+// sums and every merge (tiles -> lanes -> depth -> joint -> CTA splits) are fp64 re-scaled by exact
+// powers of two: no transcendental and no rounding in any merge weight.  The only fp32 roundings are
+// ex2.approx per element and the short per-tile sums, which keeps the result within 1e-3 mm of the
+// float64 oracle.
 // When a crop is split over several CTAs the last CTA to finish (ticket counter) merges the
 // per-split records; the workspace counters are left zeroed for the next launch.
 #include <cuda_fp16.h>
@@ -34,7 +41,10 @@ namespace metro {
 
 namespace {
 
-constexpr int kMaxThreads = 320;
+constexpr int kMaxThreads = 512;
+constexpr int kStages = 2;
+constexpr int kGroup = 8;            // pixel steps per fp32 partial sum (first level)
+constexpr int kMaxSteps = 32;        // pixel steps per thread per tile
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNone = -3.0e38f;   // exponent of an empty record
 
@@ -42,22 +52,18 @@ template <int VEC>
 struct Vec;
 template <>
 struct Vec<4> {  // 4 x fp32
-  static __device__ __forceinline__ void load(const unsigned char *p, float (&x)[4]) {
+  static __device__ __forceinline__ void load(const unsigned char *p, float2 (&x)[2]) {
     const float4 v = *reinterpret_cast<const float4 *>(p);
-    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    x[0] = make_float2(v.x, v.y); x[1] = make_float2(v.z, v.w);
   }
 };
 template <>
 struct Vec<8> {  // 8 x fp16
-  static __device__ __forceinline__ void load(const unsigned char *p, float (&x)[8]) {
+  static __device__ __forceinline__ void load(const unsigned char *p, float2 (&x)[4]) {
     const uint4 r = *reinterpret_cast<const uint4 *>(p);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
-      x[2 * i] = f.x;
-      x[2 * i + 1] = f.y;
-    }
+    for (int i = 0; i < 4; ++i) x[i] = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
   }
 };
 
@@ -66,162 +72,269 @@ __device__ __forceinline__ double pow2_neg(float d) {
   const int e = int(fmaxf(d, -1000.f));
   return __longlong_as_double((long long)(1023 + e) << 52);
 }
+__device__ __forceinline__ double shfl_xor_f64(double v, int o) {
+  return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o),
+                          __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
+}
 
-struct ChanRec {  // one channel of this CTA's pixel range
+struct ChanRec {  // one channel of one work item
   double s, sx, sy;
   float k;
   float pad;
 };
 
-template <int VEC>
-__global__ void __launch_bounds__(kMaxThreads, 4) softargmax_kernel(const SoftargmaxLaunch p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int img = blockIdx.x / p.splits, split = blockIdx.x - img * p.splits;
-  const int slot = tid % p.slots, lane = tid / p.slots;
-  const int C = p.C, J = p.J, P = p.H * p.W;
-  const int p_begin = split * p.ppc;
-  const int n_px = min(P, p_begin + p.ppc) - p_begin;
-  const int c0 = slot * VEC;
-  constexpr int esize = (VEC == 8) ? 2 : 4;
-  const int row_bytes = C * esize;
+// walks the tiles of the work items a CTA owns: item = blockIdx.x, + gridDim.x, ...; the tiles of a
+// crop are split evenly over its `splits` items
+struct Cursor {
+  int item, t, t1;
+  __device__ __forceinline__ void open(int it, int n_items, int splits, int tiles) {
+    item = it;
+    if (it < n_items) {
+      const int sp = it % splits;
+      t = sp * tiles / splits;
+      t1 = (sp + 1) * tiles / splits;
+    } else { t = t1 = 0; }
+  }
+  __device__ __forceinline__ bool done(int n_items) const { return item >= n_items; }
+};
 
-  // shared memory: [tile | records (aliases the tile once it has been consumed)] [channel records] [coords] [barrier]
-  unsigned char *s_tile = smem_raw;
-  float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);                          // [lanes][C] (k, s, sx, sy)
+template <int VEC, int LANES>
+__global__ void __launch_bounds__(kMaxThreads) softargmax_kernel(const SoftargmaxLaunch p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int V2 = VEC / 2;
+  constexpr int esize = (VEC == 8) ? 2 : 4;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int slot = tid / LANES, lane = tid % LANES;
+  const bool live = slot < p.slots;                    // the last warp is padded with idle threads
+  const int C = p.C, J = p.J, P = p.H * p.W;
+  const int c0 = slot * VEC;
+  const int row_bytes = C * esize;
+  const int tile_bytes = p.ppc * row_bytes;
+  const int n_items = p.n * p.splits;
+
+  unsigned char *s_ring = smem_raw;                                              // [kStages][tile]
+  float2 *s_hw = reinterpret_cast<float2 *>(smem_raw + p.off_hw);                // [ppc] (row in tile, column)
   ChanRec *s_ch = reinterpret_cast<ChanRec *>(smem_raw + p.off_ch);              // [C]
   double *s_c01 = reinterpret_cast<double *>(s_ch + C);                          // [J][3]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(s_c01 + 3 * J);
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_c01 + 3 * J);                  // [kStages]
   __shared__ int s_is_last;
 
-  // ---- one bulk copy of this CTA's contiguous pixel range ----------------------------------------------
-  if (tid == 0) {
-    ptx::mbar_init(bar, 1);
-    ptx::fence_mbar_init();
-    const uint32_t bytes = uint32_t(n_px) * row_bytes;
-    const unsigned char *src = static_cast<const unsigned char *>(p.head) + (size_t(img) * P + p_begin) * row_bytes;
-    ptx::mbar_arrive_expect_tx(bar, bytes);
-    ptx::bulk_load_1d(s_tile, src, bytes, bar);
-  }
-  __syncthreads();                       // barrier initialised before anyone polls it
-  ptx::mbar_wait(bar, 0);
+  auto issue = [&](const Cursor &c, int stage) {     // thread 0 only
+    const int px0 = c.t * p.ppc;
+    const uint32_t bytes = uint32_t(min(p.ppc, P - px0)) * row_bytes;
+    const unsigned char *src = static_cast<const unsigned char *>(p.head) +
+                               (size_t(c.item / p.splits) * P + px0) * row_bytes;
+    ptx::mbar_arrive_expect_tx(full + stage, bytes);
+    ptx::bulk_load_1d(s_ring + size_t(stage) * tile_bytes, src, bytes, full + stage);
+  };
+  auto advance = [&](Cursor &c) {
+    if (++c.t >= c.t1) c.open(c.item + gridDim.x, n_items, p.splits, p.tiles);
+  };
 
-  // ---- per (thread, channel): integer exponent >= max*log2e, then exp once per element --------------
-  const unsigned char *mine = s_tile + size_t(lane) * row_bytes + size_t(c0) * esize;
-  const int step = p.lanes * row_bytes;
-  const int n_mine = lane < n_px ? (n_px - lane + p.lanes - 1) / p.lanes : 0;
-  float k[VEC], s[VEC], sx[VEC], sy[VEC];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) { k[v] = -INFINITY; s[v] = sx[v] = sy[v] = 0.f; }
-  for (int r = 0; r < n_mine; ++r) {
-    float x[VEC];
-    Vec<VEC>::load(mine + size_t(r) * step, x);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) k[v] = fmaxf(k[v], x[v]);
+  Cursor prod, cons;
+  cons.open(blockIdx.x, n_items, p.splits, p.tiles);
+  prod = cons;
+  if (tid == 0) {
+    for (int st = 0; st < kStages; ++st) ptx::mbar_init(full + st, 1);
+    ptx::fence_mbar_init();
+    for (int st = 0; st < kStages && !prod.done(n_items); ++st) { issue(prod, st); advance(prod); }
   }
+  for (int q = tid; q < p.ppc; q += nthreads) {
+    const int h = q / p.W;
+    s_hw[q] = make_float2(float(h), float(q - h * p.W));
+  }
+  __syncthreads();                       // barriers initialised and the (row, column) table written
+
+  // running record of this thread's channels over the current item
+  double S[VEC], SX[VEC], SY[VEC];
+  float K[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) k[v] = (k[v] == -INFINITY) ? kNone : ceilf(k[v] * kLog2e);
-  {
-    int q = p_begin + lane;
-    for (int r = 0; r < n_mine; ++r, q += p.lanes) {
-      float x[VEC];
-      Vec<VEC>::load(mine + size_t(r) * step, x);
-      const int h = q / p.W;
-      const float fh = float(h), fw = float(q - h * p.W);
+  for (int v = 0; v < VEC; ++v) { S[v] = SX[v] = SY[v] = 0.0; K[v] = kNone; }
+  const float2 l2e = make_float2(kLog2e, kLog2e);
+  const int step_bytes = LANES * row_bytes;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  while (!cons.done(n_items)) {
+    const int px0 = cons.t * p.ppc;
+    const int steps = min(p.ppc, P - px0) / LANES;       // whole rows: a multiple of LANES
+    const float h0 = float(px0 / p.W);
+    ptx::mbar_wait(full + stage, phase);
+    if (live) {
+      const unsigned char *ptr = s_ring + size_t(stage) * tile_bytes + size_t(lane) * row_bytes + size_t(c0) * esize;
+      // pass 1: this thread's maximum per channel over the tile -> integer exponent
+      float2 m[V2];
+#pragma unroll
+      for (int v = 0; v < V2; ++v) m[v] = make_float2(-INFINITY, -INFINITY);
+#pragma unroll 8
+      for (int i = 0; i < steps; ++i) {
+        float2 x[V2];
+        Vec<VEC>::load(ptr + i * step_bytes, x);
+#pragma unroll
+        for (int v = 0; v < V2; ++v) { m[v].x = fmaxf(m[v].x, x[v].x); m[v].y = fmaxf(m[v].y, x[v].y); }
+      }
+      float2 nk[V2];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float e = ptx::ex2_approx(fmaf(x[v], kLog2e, -k[v]));
-        s[v] += e;
-        sx[v] = fmaf(e, fw, sx[v]);
-        sy[v] = fmaf(e, fh, sy[v]);
+        const float kt = ceilf(((v & 1) ? m[v >> 1].y : m[v >> 1].x) * kLog2e);
+        if (kt > K[v]) {                                 // raise the exponent: exact re-scale of the running sums
+          const double r = pow2_neg(K[v] - kt);
+          S[v] *= r; SX[v] *= r; SY[v] *= r;
+          K[v] = kt;
+        }
+        if (v & 1) nk[v >> 1].y = -K[v]; else nk[v >> 1].x = -K[v];
       }
-    }
-  }
-  __syncthreads();                       // the tile is consumed; its space becomes the record array
+      // pass 2: exp once per element; fp32 partial sums of kGroup terms, then of groups
+      float2 ts[V2], tx[V2], ty[V2];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) s_rec[size_t(lane) * C + c0 + v] = make_float4(k[v], s[v], sx[v], sy[v]);
-  __syncthreads();
-
-  // ---- pixel lanes -> channel (exact power-of-two re-scaling, fp64 sums) ---------------------------
-  for (int c = tid; c < C; c += nthreads) {
-    float kk = kNone;
-    for (int l = 0; l < p.lanes; ++l) kk = fmaxf(kk, s_rec[size_t(l) * C + c].x);
-    double a = 0.0, ax = 0.0, ay = 0.0;
-    for (int l = 0; l < p.lanes; ++l) {
-      const float4 r = s_rec[size_t(l) * C + c];
-      const double wgt = pow2_neg(r.x - kk);
-      a += wgt * double(r.y); ax += wgt * double(r.z); ay += wgt * double(r.w);
-    }
-    ChanRec o; o.s = a; o.sx = ax; o.sy = ay; o.k = kk; o.pad = 0.f;
-    s_ch[c] = o;
-  }
-  __syncthreads();
-
-  // ---- depth -> joint ----------------------------------------------------------------------------
-  double S = 0.0, SX = 0.0, SY = 0.0, SZ = 0.0;
-  float K = kNone;
-  if (tid < J) {
-    for (int d = 0; d < p.D; ++d) K = fmaxf(K, s_ch[d * J + tid].k);
-    for (int d = 0; d < p.D; ++d) {
-      const ChanRec r = s_ch[d * J + tid];
-      const double wgt = pow2_neg(r.k - K);
-      S += wgt * r.s; SX += wgt * r.sx; SY += wgt * r.sy; SZ += double(d) * (wgt * r.s);
-    }
-  }
-
-  if (p.splits > 1) {
-    // publish this split's record; the last CTA of the crop merges them.  bar.sync orders the J
-    // writers before thread 0, whose gpu-scope fence is cumulative over what it has observed.
-    if (tid < J) {
-      double *rec = p.partials + ((size_t(img) * p.splits + split) * J + tid) * 5;
-      rec[0] = double(K); rec[1] = S; rec[2] = SX; rec[3] = SY; rec[4] = SZ;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      const unsigned int ticket = atomicAdd(p.counters + img, 1u);
-      s_is_last = (ticket == unsigned(p.splits - 1));
-      if (s_is_last) __threadfence();
-    }
-    __syncthreads();
-    if (!s_is_last) return;
-    if (tid < J) {
-      const double *recs = p.partials + (size_t(img) * p.splits) * J * 5;
-      double gk = double(kNone);
-      for (int sp = 0; sp < p.splits; ++sp) gk = fmax(gk, __ldcg(recs + (size_t(sp) * J + tid) * 5));
-      S = SX = SY = SZ = 0.0;
-      for (int sp = 0; sp < p.splits; ++sp) {
-        const double *rec = recs + (size_t(sp) * J + tid) * 5;
-        const double wgt = pow2_neg(float(__ldcg(rec) - gk));
-        S += wgt * __ldcg(rec + 1); SX += wgt * __ldcg(rec + 2);
-        SY += wgt * __ldcg(rec + 3); SZ += wgt * __ldcg(rec + 4);
+      for (int v = 0; v < V2; ++v) ts[v] = tx[v] = ty[v] = make_float2(0.f, 0.f);
+      const float2 *hw = s_hw + lane;
+      for (int i0 = 0; i0 < steps; i0 += kGroup) {
+        float2 gs[V2], gx[V2], gy[V2];
+#pragma unroll
+        for (int v = 0; v < V2; ++v) gs[v] = gx[v] = gy[v] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int ii = 0; ii < kGroup; ++ii) {
+          const int i = i0 + ii;
+          if (i < steps) {
+            float2 x[V2];
+            Vec<VEC>::load(ptr + i * step_bytes, x);
+            const float2 rc = hw[i * LANES];
+            const float fh = rc.x + h0;
+            const float2 fh2 = make_float2(fh, fh), fw2 = make_float2(rc.y, rc.y);
+#pragma unroll
+            for (int v = 0; v < V2; ++v) {
+              const float2 t = __ffma2_rn(x[v], l2e, nk[v]);
+              const float2 e = make_float2(ptx::ex2_approx(t.x), ptx::ex2_approx(t.y));
+              gs[v] = __fadd2_rn(gs[v], e);
+              gx[v] = __ffma2_rn(e, fw2, gx[v]);
+              gy[v] = __ffma2_rn(e, fh2, gy[v]);
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V2; ++v) {
+          ts[v] = __fadd2_rn(ts[v], gs[v]); tx[v] = __fadd2_rn(tx[v], gx[v]); ty[v] = __fadd2_rn(ty[v], gy[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        S[v] += double((v & 1) ? ts[v >> 1].y : ts[v >> 1].x);
+        SX[v] += double((v & 1) ? tx[v >> 1].y : tx[v >> 1].x);
+        SY[v] += double((v & 1) ? ty[v >> 1].y : ty[v >> 1].x);
       }
     }
-    if (tid == 0) p.counters[img] = 0;   // self-cleaning for the next launch
-  }
+    __syncthreads();                     // every thread is done with this ring stage
+    if (tid == 0 && !prod.done(n_items)) { issue(prod, stage); advance(prod); }
+    if (++stage == kStages) { stage = 0; phase ^= 1; }
+    const int item = cons.item;
+    const bool item_done = (cons.t + 1 >= cons.t1);
+    advance(cons);
+    if (!item_done) continue;
 
-  // expectation of linspace(0,1,n) along each axis == E[index]/(n-1); mul_* carry 1/(n-1) and mm
-  if (tid < J) {
-    const double inv = 1.0 / S;
-    s_c01[3 * tid] = SX * inv * p.mul_x;
-    s_c01[3 * tid + 1] = SY * inv * p.mul_y;
-    s_c01[3 * tid + 2] = SZ * inv * p.mul_z;
-  }
-  __syncthreads();
-  for (int i = tid; i < p.n_out * 3; i += nthreads) {
-    const int jo = i / 3, a = i - 3 * jo;
-    p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
+    // ======================= end of a work item: merge and publish =======================
+    const int img = item / p.splits, split = item - img * p.splits;
+    // pixel lanes -> channel: the lanes of a slot sit in one warp; exact re-scaling, fp64 sums
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float kk = K[v];
+#pragma unroll
+      for (int o = LANES / 2; o >= 1; o >>= 1) kk = fmaxf(kk, __shfl_xor_sync(0xffffffffu, kk, o));
+      const double wgt = pow2_neg(K[v] - kk);
+      double a = wgt * S[v], ax = wgt * SX[v], ay = wgt * SY[v];
+#pragma unroll
+      for (int o = LANES / 2; o >= 1; o >>= 1) {
+        a += shfl_xor_f64(a, o); ax += shfl_xor_f64(ax, o); ay += shfl_xor_f64(ay, o);
+      }
+      if (live && lane == 0) {
+        ChanRec o; o.s = a; o.sx = ax; o.sy = ay; o.k = kk; o.pad = 0.f;
+        s_ch[c0 + v] = o;
+      }
+      S[v] = SX[v] = SY[v] = 0.0; K[v] = kNone;        // reset for the next item
+    }
+    __syncthreads();
+    // depth -> joint
+    double TS = 0.0, TX = 0.0, TY = 0.0, TZ = 0.0;
+    float TK = kNone;
+    if (tid < J) {
+      for (int d = 0; d < p.D; ++d) TK = fmaxf(TK, s_ch[d * J + tid].k);
+      for (int d = 0; d < p.D; ++d) {
+        const ChanRec r = s_ch[d * J + tid];
+        const double wgt = pow2_neg(r.k - TK);
+        TS += wgt * r.s; TX += wgt * r.sx; TY += wgt * r.sy; TZ += double(d) * (wgt * r.s);
+      }
+    }
+    bool publish = true;
+    if (p.splits > 1) {
+      // publish this split's record; the last CTA of the crop merges them.  bar.sync orders the J
+      // writers before thread 0, whose gpu-scope fence is cumulative over what it has observed.
+      if (tid < J) {
+        double *rec = p.partials + ((size_t(img) * p.splits + split) * J + tid) * 5;
+        rec[0] = double(TK); rec[1] = TS; rec[2] = TX; rec[3] = TY; rec[4] = TZ;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(p.counters + img, 1u);
+        s_is_last = (ticket == unsigned(p.splits - 1));
+        if (s_is_last) __threadfence();
+      }
+      __syncthreads();
+      publish = s_is_last != 0;
+      if (publish && tid < J) {
+        const double *recs = p.partials + (size_t(img) * p.splits) * J * 5;
+        double gk = double(kNone);
+        for (int sp = 0; sp < p.splits; ++sp) gk = fmax(gk, __ldcg(recs + (size_t(sp) * J + tid) * 5));
+        TS = TX = TY = TZ = 0.0;
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const double *rec = recs + (size_t(sp) * J + tid) * 5;
+          const double wgt = pow2_neg(float(__ldcg(rec) - gk));
+          TS += wgt * __ldcg(rec + 1); TX += wgt * __ldcg(rec + 2);
+          TY += wgt * __ldcg(rec + 3); TZ += wgt * __ldcg(rec + 4);
+        }
+      }
+      if (publish && tid == 0) p.counters[img] = 0;   // self-cleaning for the next launch
+    }
+    if (publish) {
+      // expectation of linspace(0,1,n) along each axis == E[index]/(n-1); mul_* carry 1/(n-1) and mm
+      if (tid < J) {
+        const double inv = 1.0 / TS;
+        s_c01[3 * tid] = TX * inv * p.mul_x;
+        s_c01[3 * tid + 1] = TY * inv * p.mul_y;
+        s_c01[3 * tid + 2] = TZ * inv * p.mul_z;
+      }
+      __syncthreads();
+      for (int i = tid; i < p.n_out * 3; i += nthreads) {
+        const int jo = i / 3, a = i - 3 * jo;
+        p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
+      }
+    }
+    __syncthreads();                     // s_ch / s_c01 / s_is_last are reused by the next item
   }
 }
 
-size_t tile_region_bytes(const SoftargmaxLaunch &L) {
-  const size_t tile = size_t(L.ppc) * L.C * (L.head_f16 ? 2 : 4);
-  const size_t rec = size_t(L.lanes) * L.C * 16;
-  return ((tile > rec ? tile : rec) + 127) & ~size_t(127);
+size_t tile_bytes(const SoftargmaxLaunch &L) {
+  return (size_t(L.ppc) * L.C * (L.head_f16 ? 2 : 4) + 127) & ~size_t(127);
 }
+size_t hw_bytes(const SoftargmaxLaunch &L) { return (size_t(L.ppc) * 8 + 127) & ~size_t(127); }
 
 size_t smem_bytes(const SoftargmaxLaunch &L) {
-  return tile_region_bytes(L) + size_t(L.C) * sizeof(ChanRec) + size_t(3) * L.J * 8 + 16;
+  return kStages * tile_bytes(L) + hw_bytes(L) + size_t(L.C) * sizeof(ChanRec) + size_t(3) * L.J * 8 + kStages * 8 + 16;
+}
+
+template <int VEC, int LANES>
+metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
+  static size_t configured = 0;
+  const size_t sm = smem_bytes(L);
+  if (configured < sm) {
+    METRO_CUDA(cudaFuncSetAttribute(softargmax_kernel<VEC, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  const int n_items = L.n * L.splits;
+  const dim3 grid(unsigned(n_items < L.max_ctas ? n_items : L.max_ctas)), block(unsigned((L.slots * L.lanes + 31) & ~31));
+  softargmax_kernel<VEC, LANES><<<grid, block, sm, stream>>>(L);
+  METRO_CUDA(cudaGetLastError());
+  return METRO_OK;
 }
 
 }  // namespace
@@ -255,23 +368,36 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   L.slots = L.C / vec;
   if (L.slots > kMaxThreads) return fail(METRO_ERR_VALUE, "softargmax: too many head channels (%d)", L.C);
   const int P = L.H * L.W;
-  // CTA shape: `lanes` pixel lanes x `slots` 16-byte channel slots; the CTA's tile is `ppc` pixels
-  // (~35 KB by default, so ~5 CTAs = ~175 KB of copies are in flight per SM).
-  int lanes = d.lanes > 0 ? d.lanes : 8;
-  if (lanes > P) lanes = P;
-  while (lanes > 1 && lanes * L.slots > kMaxThreads) --lanes;
+  // CTA shape: `slots` 16-byte channel slots x `lanes` pixel lanes (a power of two dividing W, so whole
+  // rows split evenly over the lanes and the lanes of a slot share a warp).  Tiles are whole rows,
+  // ~35 KB; a 2-stage ring per CTA and 2-3 CTAs per SM keep ~150 KB of copies in flight per SM.
+  int lanes = d.lanes > 0 ? d.lanes : 4;
+  while (lanes > 1 && (lanes > 8 || (lanes & (lanes - 1)) != 0 || L.W % lanes != 0 ||
+                       ((L.slots * lanes + 31) & ~31) > kMaxThreads)) --lanes;
+  if (((L.slots * lanes + 31) & ~31) > kMaxThreads) return fail(METRO_ERR_VALUE, "softargmax: too many head channels (%d)", L.C);
   L.lanes = lanes;
   const int row_bytes = L.C * (L.head_f16 ? 2 : 4);
-  int ppc_max = (40 * 1024) / row_bytes;                 // tile budget
-  if (ppc_max < lanes) ppc_max = lanes;
-  int splits = d.splits > 0 ? d.splits : (P * row_bytes + 36 * 1024 - 1) / (36 * 1024);
-  if (splits < (P + ppc_max - 1) / ppc_max) splits = (P + ppc_max - 1) / ppc_max;
-  if (splits > P) splits = P;
-  L.ppc = (P + splits - 1) / splits;
-  L.splits = (P + L.ppc - 1) / L.ppc;
-  L.rpt = (L.ppc + lanes - 1) / lanes;
-  L.off_ch = int(tile_region_bytes(L));
-  if (smem_bytes(L) > 48 * 1024) return fail(METRO_ERR_VALUE, "softargmax: shared memory budget exceeded");
+  int rows = (36 * 1024) / (row_bytes * L.W);                         // tile budget
+  if (rows > kMaxSteps * lanes / L.W) rows = kMaxSteps * lanes / L.W;  // bounded per-thread partial sums
+  if (rows > L.H) rows = L.H;
+  if (rows < 1) {
+    if (size_t(row_bytes) * L.W > 96 * 1024) return fail(METRO_ERR_VALUE, "softargmax: one heatmap row (%d bytes) exceeds the tile budget", row_bytes * L.W);
+    rows = 1;
+  }
+  L.ppc = rows * L.W;
+  L.tiles = (L.H + rows - 1) / rows;
+  // work items: one per crop unless the batch is too small to occupy the GPU, then a crop's tiles are
+  // split over several CTAs (merged by the last one to finish)
+  const int slots_gpu = 148 * 2;
+  int splits = d.splits > 0 ? d.splits : (n > 0 ? slots_gpu / n : 1);
+  if (splits < 1) splits = 1;
+  if (splits > L.tiles) splits = L.tiles;
+  L.splits = splits;
+  L.max_ctas = 148 * 3;
+  L.rpt = L.ppc / lanes;
+  L.off_hw = int(kStages * tile_bytes(L));
+  L.off_ch = L.off_hw + int(hw_bytes(L));
+  if (smem_bytes(L) > 200 * 1024) return fail(METRO_ERR_VALUE, "softargmax: shared memory budget exceeded");
   return METRO_OK;
 }
 
@@ -282,12 +408,24 @@ size_t softargmax_workspace_bytes(const SoftargmaxLaunch &L) {
 
 metro_status softargmax_launch(const SoftargmaxLaunch &L, cudaStream_t stream) {
   if (L.n == 0) return METRO_OK;
-  const dim3 grid(unsigned(L.n) * L.splits), block(unsigned(L.slots) * L.lanes);
-  const size_t sm = smem_bytes(L);
-  if (L.head_f16) softargmax_kernel<8><<<grid, block, sm, stream>>>(L);
-  else softargmax_kernel<4><<<grid, block, sm, stream>>>(L);
-  METRO_CUDA(cudaGetLastError());
-  return METRO_OK;
+#define METRO_SAM(V, LN) return launch_t<V, LN>(L, stream)
+  if (L.head_f16) {
+    switch (L.lanes) {
+      case 1: METRO_SAM(8, 1);
+      case 2: METRO_SAM(8, 2);
+      case 4: METRO_SAM(8, 4);
+      case 8: METRO_SAM(8, 8);
+    }
+  } else {
+    switch (L.lanes) {
+      case 1: METRO_SAM(4, 1);
+      case 2: METRO_SAM(4, 2);
+      case 4: METRO_SAM(4, 4);
+      case 8: METRO_SAM(4, 8);
+    }
+  }
+#undef METRO_SAM
+  return fail(METRO_ERR_INTERNAL, "softargmax: %d lanes not instantiated", L.lanes);
 }
 
 }  // namespace metro

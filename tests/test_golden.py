@@ -1,0 +1,154 @@
+"""Pins the oracle (oracle/metro_oracle.py, oracle/decode_ref.c), the layer plan (spec.py) and the
+joint tables (joints.py) against tests/golden/*.npz -- vectors produced by EXECUTING THE REFERENCE'S
+OWN PYTHON graph builders over a float64 op shim (oracle/gen_golden.py, oracle/tf_shim.py; generated
+in the build container where /root/reference is mounted, committed because the reference cannot
+travel).  Nothing here reads /root/reference.
+
+The fixtures hold outputs only; inputs are regenerated from the seeds they record."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from metro_pose3d_b200.joints import export_permutation, exported_joint_info, model_joint_info
+from metro_pose3d_b200.spec import NetSpec
+from metro_pose3d_b200.weights import blob_order, synth_head, synth_images, synth_weights
+from oracle.metro_oracle import OracleNet, decode_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+DECODE_CASES = {'A': 'h36m', 'B': 'h36m', 'C': 'coco19', 'D': 'coco19', 'E': 'coco19', 'M': 'merged'}
+NETS = ['rn50_s32', 'rn50_s16', 'rn50_s8', 'rn50_s4', 'rn101_s16', 'rn101_s4', 'rn50_s16_nocenter', 'rn101_s32']
+
+
+def _arch(name):
+    return 'resnet_v2_101' if name.startswith('rn101') else 'resnet_v2_50'
+
+
+def test_joint_tables_match_the_reference_classes():
+    g = np.load(os.path.join(GOLD, 'joints.npz'))
+    for ds in ('h36m', 'merged'):
+        ji = model_joint_info(ds)
+        assert list(g[f'{ds}_model_names']) == ji.names
+        assert [tuple(e) for e in g[f'{ds}_model_edges']] == [tuple(e) for e in ji.edges]
+        assert list(g[f'{ds}_permutation']) == export_permutation(ds)
+    ex = exported_joint_info('h36m')
+    assert list(g['h36m_export_names']) == ex.names
+    assert [tuple(e) for e in g['h36m_export_edges']] == [tuple(e) for e in ex.edges]
+    # BASELINE's 19-joint head uses the merged export permutation
+    assert export_permutation('coco19') == list(g['merged_permutation'])
+
+
+@pytest.mark.parametrize('case', sorted(DECODE_CASES))
+def test_decode_oracles_match_reference_code(case):
+    """volumetric.net_output_to_heatmap_and_coords + heatmap_to_metric + root_relative + gather as run
+    from the reference's files, vs the numpy restatement and the plain-C restatement."""
+    g = np.load(os.path.join(GOLD, 'decode.npz'))
+    n, side, stride, j, seed = (int(v) for v in g[f'{case}_meta'])
+    perm = export_permutation(DECODE_CASES[case])
+    head = synth_head(n, side, j, seed=seed)
+    want = g[f'{case}_poses']
+    got = decode_ref(head, j, stride, perm)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-9
+    c01 = decode_ref(head, j, stride, perm, return_coords01=True)
+    assert np.abs(c01 - g[f'{case}_coords01']).max() < 1e-12
+    subprocess.run(['make', '-C', os.path.join(ROOT, 'oracle'), '-s'], check=True)
+    lib = C.CDLL(os.path.join(ROOT, 'oracle', '_build', 'libdecode_ref.so'))
+    out = np.zeros((n, len(perm), 3))
+    p = (C.c_int * len(perm))(*perm)
+    rc = lib.metro_oracle_decode(head.ctypes.data_as(C.c_void_p), n, side, j, 8, stride, 1, 256, C.c_double(2200.0), p,
+                                 len(perm), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0 and np.abs(out - want).max() < 1e-9
+
+
+_LAYER_KEY = {'conv1': '{p}conv1', 'pool1': '{p}pool1', 'postnorm': '{p}postnorm'}
+
+
+@pytest.mark.parametrize('name', NETS)
+def test_graph_oracle_matches_reference_code(name):
+    """Whole exported graph (main.export -> build_inference_model -> architectures.resnet ->
+    resnet_v2 / resnet_utils -> decode) as run from the reference's files, vs the oracle in float64:
+    poses, every convolution / pooling / normalisation output (rms, sum and a probe slice), and the
+    variable set the graph creates (names + shapes) vs weights.blob_order."""
+    g = np.load(os.path.join(GOLD, 'graph.npz'))
+    n, side, stride, j, centered, wseed, iseed = (int(v) for v in g[f'{name}_meta'])
+    arch = _arch(name)
+    spec = NetSpec(arch, stride, j, centered_stride=bool(centered), proc_side=side)
+    # variables: same set, same shapes (TF creates a unit's BatchNorm variables in beta, gamma, mean, variance order;
+    # the blob serialises gamma first -- the set and the per-variable shapes are what must agree)
+    ref_vars = dict(zip(g[f'{name}_vars'], g[f'{name}_var_shapes']))
+    mine = {k: ','.join(map(str, s)) for k, s in blob_order(spec)}
+    assert ref_vars == mine
+    w = synth_weights(spec, seed=wseed)
+    img = synth_images(n, seed=iseed, side=side)
+    ora = OracleNet(spec, w, export_permutation('h36m'), 'fp64')
+    ora.trace = {}
+    poses = ora(img)
+    want = g[f'{name}_poses']
+    assert poses.shape == want.shape
+    assert np.abs(poses - want).max() < 1e-6, np.abs(poses - want).max()
+    layers = {k: i for i, k in enumerate(g[f'{name}_layers'])}
+    p = f'MainPart/{arch}/'
+    checked = 0
+    for lname, t in ora.trace.items():
+        if lname in _LAYER_KEY:
+            key = _LAYER_KEY[lname].format(p=p)
+        elif lname.endswith('/conv1') or lname.endswith('/conv2'):
+            unit, leaf = lname.rsplit('/', 1)
+            key = f'{p}{unit}/bottleneck_v2/{leaf}'
+        else:
+            continue                                  # unit sums are not ops of their own in the reference graph
+        i = layers[key]
+        assert ','.join(map(str, t.shape)) == g[f'{name}_layer_shapes'][i], key
+        assert abs(np.sqrt(np.mean(t ** 2)) - g[f'{name}_layer_rms'][i]) < 1e-9 * max(1.0, g[f'{name}_layer_rms'][i]), key
+        assert abs(t.sum() - g[f'{name}_layer_sum'][i]) < 1e-7 * max(1.0, abs(g[f'{name}_layer_sum'][i])), key
+        probe = t[0, 0, :, :8].ravel()[:64]
+        assert np.abs(probe - g[f'{name}_layer_probe'][i][:probe.size]).max() < 1e-9, key
+        checked += 1
+    assert checked == 2 * len(spec.units) + 3
+    # head side / channels as the reference graph produced them
+    i = layers[f'{p}logits']
+    assert g[f'{name}_layer_shapes'][i] == f'{n},{spec.feat_side},{spec.feat_side},{8 * j}'
+    # conv2 geometry of every unit: the reference's output sides equal the plan's
+    for u in spec.units:
+        i = layers[f'{p}{u.name}/bottleneck_v2/conv2']
+        assert g[f'{name}_layer_shapes'][i] == f'{n},{u.out_side},{u.out_side},{u.cb}', u.name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', ['A', 'B', 'C', 'D', 'E'])
+def test_cuda_decode_matches_reference_code(case):
+    """The CUDA soft-argmax (C-ABI metro_softargmax) against the reference-code vectors: 1e-3 mm."""
+    import torch
+    from metro_pose3d_b200.inference import SoftArgmax
+    g = np.load(os.path.join(GOLD, 'decode.npz'))
+    n, side, stride, j, seed = (int(v) for v in g[f'{case}_meta'])
+    perm = export_permutation(DECODE_CASES[case])
+    head = torch.from_numpy(synth_head(n, side, j, seed=seed)).cuda()
+    got = SoftArgmax(side, j, stride, perm)(head).cpu().numpy()
+    assert np.abs(got - g[f'{case}_poses']).max() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['rn50_s32', 'rn50_s16'])
+def test_cuda_graph_against_reference_code(name):
+    """The whole CUDA path against the reference-code poses (float64 evaluation of the graph).  The
+    CUDA path computes the backbone in float16 like the reference's default (src/options.py:73), so the
+    bound is the fp16 noise floor: the distance between the float64 graph and the oracle that rounds to
+    float16 at the storage points, x1.5 + 0.25 mm."""
+    import torch
+    from metro_pose3d_b200.inference import MetroModel
+    g = np.load(os.path.join(GOLD, 'graph.npz'))
+    n, side, stride, j, centered, wseed, iseed = (int(v) for v in g[f'{name}_meta'])
+    spec = NetSpec(_arch(name), stride, j)
+    w = synth_weights(spec, seed=wseed)
+    img = synth_images(n, seed=iseed, side=side)
+    want = g[f'{name}_poses']
+    model = MetroModel(_arch(name), stride, 'h36m', weights=w, max_batch=n)
+    got = model.infer(torch.from_numpy(img).cuda()).cpu().numpy()
+    noise = np.abs(OracleNet(spec, w, export_permutation('h36m'), 'half')(img) - want).max()
+    assert np.abs(got - want).max() < 1.5 * noise + 0.25, (np.abs(got - want).max(), noise)

@@ -41,8 +41,7 @@ def stage_sam():
                 h = base.repeat((n + 7) // 8, 1, 1, 1)[:n].roll(r, 0).contiguous()
                 heads.append(h.half() if dt == 'f16' else h)
             P = side * side
-            for lanes, splits in [(0, 0), (8, max(1, P // 128)), (8, max(1, P // 64)), (8, max(1, P // 32)), (8, max(1, P // 16)),
-                                  (4, max(1, P // 64)), (4, max(1, P // 32)), (4, max(1, P // 16)), (9, max(1, P // 72))]:
+            for lanes, splits in [(0, 0), (2, 0), (4, 0), (8, 0), (4, 1), (4, 2), (4, 4), (8, 2), (2, 2)]:
                 try:
                     op = SoftArgmax(side, j, stride, perm, head_dtype=dt, splits=splits, lanes=lanes)
                     out = torch.empty((n, j, 3), device='cuda')
