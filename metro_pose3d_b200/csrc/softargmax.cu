@@ -48,22 +48,36 @@ constexpr int kMaxSteps = 32;        // pixel steps per thread per tile
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNone = -3.0e38f;   // exponent of an empty record
 
-template <int VEC>
+// VEC channels of one pixel from a 32-bit shared-memory address, as VEC/2 float pairs
+template <int VEC, bool F16>
 struct Vec;
 template <>
-struct Vec<4> {  // 4 x fp32
-  static __device__ __forceinline__ void load(const unsigned char *p, float2 (&x)[2]) {
-    const float4 v = *reinterpret_cast<const float4 *>(p);
+struct Vec<4, false> {  // 4 x fp32, 16 bytes
+  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[2]) {
+    const float4 v = ptx::lds_v4(addr);
     x[0] = make_float2(v.x, v.y); x[1] = make_float2(v.z, v.w);
   }
 };
 template <>
-struct Vec<8> {  // 8 x fp16
-  static __device__ __forceinline__ void load(const unsigned char *p, float2 (&x)[4]) {
-    const uint4 r = *reinterpret_cast<const uint4 *>(p);
+struct Vec<2, false> {  // 2 x fp32, 8 bytes
+  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[1]) { x[0] = ptx::lds_v2(addr); }
+};
+template <>
+struct Vec<8, true> {  // 8 x fp16, 16 bytes
+  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[4]) {
+    const uint4 r = ptx::lds_v4u(addr);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+  }
+};
+template <>
+struct Vec<4, true> {  // 4 x fp16, 8 bytes
+  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[2]) {
+    const float2 r = ptx::lds_v2(addr);
+    const uint32_t w[2] = {__float_as_uint(r.x), __float_as_uint(r.y)};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) x[i] = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
   }
 };
 
@@ -98,11 +112,12 @@ struct Cursor {
   __device__ __forceinline__ bool done(int n_items) const { return item >= n_items; }
 };
 
-template <int VEC, int LANES>
-__global__ void __launch_bounds__(kMaxThreads) softargmax_kernel(const SoftargmaxLaunch p) {
+// MAXT = 192: the common shapes (<= 192 threads per CTA) with up to three CTAs resident per SM
+template <int VEC, int LANES, bool F16, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 192 ? 3 : 1) softargmax_kernel(const SoftargmaxLaunch p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int V2 = VEC / 2;
-  constexpr int esize = (VEC == 8) ? 2 : 4;
+  constexpr int esize = F16 ? 2 : 4;
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int slot = tid / LANES, lane = tid % LANES;
   const bool live = slot < p.slots;                    // the last warp is padded with idle threads
@@ -151,27 +166,40 @@ __global__ void __launch_bounds__(kMaxThreads) softargmax_kernel(const Softargma
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { S[v] = SX[v] = SY[v] = 0.0; K[v] = kNone; }
   const float2 l2e = make_float2(kLog2e, kLog2e);
-  const int step_bytes = LANES * row_bytes;
+  const uint32_t step_bytes = uint32_t(LANES) * row_bytes;
   int stage = 0;
   uint32_t phase = 0;
 
   while (!cons.done(n_items)) {
     const int px0 = cons.t * p.ppc;
-    const int steps = min(p.ppc, P - px0) / LANES;       // whole rows: a multiple of LANES
-    const float h0 = float(px0 / p.W);
-    ptx::mbar_wait(full + stage, phase);
+    const int steps = min(p.ppc, P - px0) / LANES;       // whole rows or an even part of one: a multiple of LANES
+    const int hh = px0 / p.W;
+    const float h0 = float(hh), w0 = float(px0 - hh * p.W);
+    ptx::mbar_wait_sleep(full + stage, phase);
     if (live) {
-      const unsigned char *ptr = s_ring + size_t(stage) * tile_bytes + size_t(lane) * row_bytes + size_t(c0) * esize;
+      const uint32_t base = ptx::smem_u32(s_ring) + uint32_t(stage) * tile_bytes + uint32_t(lane) * row_bytes + uint32_t(c0) * esize;
+      const int groups = steps / kGroup;
       // pass 1: this thread's maximum per channel over the tile -> integer exponent
       float2 m[V2];
 #pragma unroll
       for (int v = 0; v < V2; ++v) m[v] = make_float2(-INFINITY, -INFINITY);
-#pragma unroll 8
-      for (int i = 0; i < steps; ++i) {
-        float2 x[V2];
-        Vec<VEC>::load(ptr + i * step_bytes, x);
+      {
+        uint32_t a = base;
+        for (int g = 0; g < groups; ++g) {
 #pragma unroll
-        for (int v = 0; v < V2; ++v) { m[v].x = fmaxf(m[v].x, x[v].x); m[v].y = fmaxf(m[v].y, x[v].y); }
+          for (int ii = 0; ii < kGroup; ++ii, a += step_bytes) {
+            float2 x[V2];
+            Vec<VEC, F16>::load(a, x);
+#pragma unroll
+            for (int v = 0; v < V2; ++v) { m[v].x = fmaxf(m[v].x, x[v].x); m[v].y = fmaxf(m[v].y, x[v].y); }
+          }
+        }
+        for (int i = groups * kGroup; i < steps; ++i, a += step_bytes) {
+          float2 x[V2];
+          Vec<VEC, F16>::load(a, x);
+#pragma unroll
+          for (int v = 0; v < V2; ++v) { m[v].x = fmaxf(m[v].x, x[v].x); m[v].y = fmaxf(m[v].y, x[v].y); }
+        }
       }
       float2 nk[V2];
 #pragma unroll
@@ -188,30 +216,39 @@ __global__ void __launch_bounds__(kMaxThreads) softargmax_kernel(const Softargma
       float2 ts[V2], tx[V2], ty[V2];
 #pragma unroll
       for (int v = 0; v < V2; ++v) ts[v] = tx[v] = ty[v] = make_float2(0.f, 0.f);
-      const float2 *hw = s_hw + lane;
-      for (int i0 = 0; i0 < steps; i0 += kGroup) {
+      uint32_t a = base;
+      uint32_t hwa = ptx::smem_u32(s_hw) + uint32_t(lane) * 8;
+      auto step = [&](uint32_t xa, uint32_t ha, float2 (&gs)[V2], float2 (&gx)[V2], float2 (&gy)[V2]) {
+        float2 x[V2];
+        Vec<VEC, F16>::load(xa, x);
+        const float2 rc = ptx::lds_v2(ha);
+        const float fh = rc.x + h0, fw = rc.y + w0;
+        const float2 fh2 = make_float2(fh, fh), fw2 = make_float2(fw, fw);
+#pragma unroll
+        for (int v = 0; v < V2; ++v) {
+          const float2 t = __ffma2_rn(x[v], l2e, nk[v]);
+          const float2 e = make_float2(ptx::ex2_approx(t.x), ptx::ex2_approx(t.y));
+          gs[v] = __fadd2_rn(gs[v], e);
+          gx[v] = __ffma2_rn(e, fw2, gx[v]);
+          gy[v] = __ffma2_rn(e, fh2, gy[v]);
+        }
+      };
+      for (int g = 0; g < groups; ++g, hwa += kGroup * LANES * 8) {
         float2 gs[V2], gx[V2], gy[V2];
 #pragma unroll
         for (int v = 0; v < V2; ++v) gs[v] = gx[v] = gy[v] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int ii = 0; ii < kGroup; ++ii) {
-          const int i = i0 + ii;
-          if (i < steps) {
-            float2 x[V2];
-            Vec<VEC>::load(ptr + i * step_bytes, x);
-            const float2 rc = hw[i * LANES];
-            const float fh = rc.x + h0;
-            const float2 fh2 = make_float2(fh, fh), fw2 = make_float2(rc.y, rc.y);
+        for (int ii = 0; ii < kGroup; ++ii, a += step_bytes) step(a, hwa + ii * LANES * 8, gs, gx, gy);
 #pragma unroll
-            for (int v = 0; v < V2; ++v) {
-              const float2 t = __ffma2_rn(x[v], l2e, nk[v]);
-              const float2 e = make_float2(ptx::ex2_approx(t.x), ptx::ex2_approx(t.y));
-              gs[v] = __fadd2_rn(gs[v], e);
-              gx[v] = __ffma2_rn(e, fw2, gx[v]);
-              gy[v] = __ffma2_rn(e, fh2, gy[v]);
-            }
-          }
+        for (int v = 0; v < V2; ++v) {
+          ts[v] = __fadd2_rn(ts[v], gs[v]); tx[v] = __fadd2_rn(tx[v], gx[v]); ty[v] = __fadd2_rn(ty[v], gy[v]);
         }
+      }
+      if (groups * kGroup < steps) {
+        float2 gs[V2], gx[V2], gy[V2];
+#pragma unroll
+        for (int v = 0; v < V2; ++v) gs[v] = gx[v] = gy[v] = make_float2(0.f, 0.f);
+        for (int i = groups * kGroup; i < steps; ++i, a += step_bytes, hwa += LANES * 8) step(a, hwa, gs, gx, gy);
 #pragma unroll
         for (int v = 0; v < V2; ++v) {
           ts[v] = __fadd2_rn(ts[v], gs[v]); tx[v] = __fadd2_rn(tx[v], gx[v]); ty[v] = __fadd2_rn(ty[v], gy[v]);
@@ -322,17 +359,17 @@ size_t smem_bytes(const SoftargmaxLaunch &L) {
   return kStages * tile_bytes(L) + hw_bytes(L) + size_t(L.C) * sizeof(ChanRec) + size_t(3) * L.J * 8 + kStages * 8 + 16;
 }
 
-template <int VEC, int LANES>
+template <int VEC, int LANES, bool F16, int MAXT>
 metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
   static size_t configured = 0;
   const size_t sm = smem_bytes(L);
   if (configured < sm) {
-    METRO_CUDA(cudaFuncSetAttribute(softargmax_kernel<VEC, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    METRO_CUDA(cudaFuncSetAttribute(softargmax_kernel<VEC, LANES, F16, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = 200 * 1024;
   }
   const int n_items = L.n * L.splits;
   const dim3 grid(unsigned(n_items < L.max_ctas ? n_items : L.max_ctas)), block(unsigned((L.slots * L.lanes + 31) & ~31));
-  softargmax_kernel<VEC, LANES><<<grid, block, sm, stream>>>(L);
+  softargmax_kernel<VEC, LANES, F16, MAXT><<<grid, block, sm, stream>>>(L);
   METRO_CUDA(cudaGetLastError());
   return METRO_OK;
 }
@@ -345,7 +382,12 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   if (d.n_joints_out > kMaxJointsOut) return fail(METRO_ERR_VALUE, "softargmax: n_joints_out > %d", kMaxJointsOut);
   if (d.stride <= 0 || d.proc_side <= 0) return fail(METRO_ERR_VALUE, "softargmax: stride and proc_side must be positive");
   if (n < 0) return fail(METRO_ERR_VALUE, "softargmax: negative batch");
-  const int vec = d.head_dtype == METRO_F16 ? 8 : 4;
+  // a thread owns one 16-byte word of a pixel (4 fp32 / 8 fp16 channels); 8-byte words when the channel
+  // count is not a multiple of that
+  const bool f16 = d.head_dtype == METRO_F16;
+  if (d.word_bytes != 0 && d.word_bytes != 8 && d.word_bytes != 16) return fail(METRO_ERR_VALUE, "softargmax: word_bytes must be 0, 8 or 16");
+  int vec = (d.word_bytes == 8 ? 8 : 16) / (f16 ? 2 : 4);
+  if (d.word_bytes == 0 && (d.n_joints_model * d.depth) % vec != 0) vec /= 2;
   if (d.head_dtype != METRO_F16 && d.head_dtype != METRO_F32) return fail(METRO_ERR_VALUE, "softargmax: bad head_dtype");
   L = SoftargmaxLaunch();
   L.n = n; L.H = L.W = d.side; L.J = d.n_joints_model; L.D = d.depth; L.C = L.J * L.D;
@@ -366,6 +408,7 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   L.mul_z = L.D > 1 ? double(d.box_size_mm) / double(L.D - 1) : 0.0;
   L.head_f16 = d.head_dtype == METRO_F16;
   L.slots = L.C / vec;
+  L.vec = vec;
   if (L.slots > kMaxThreads) return fail(METRO_ERR_VALUE, "softargmax: too many head channels (%d)", L.C);
   const int P = L.H * L.W;
   // CTA shape: `slots` 16-byte channel slots x `lanes` pixel lanes (a power of two dividing W, so whole
@@ -377,19 +420,30 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   if (((L.slots * lanes + 31) & ~31) > kMaxThreads) return fail(METRO_ERR_VALUE, "softargmax: too many head channels (%d)", L.C);
   L.lanes = lanes;
   const int row_bytes = L.C * (L.head_f16 ? 2 : 4);
-  int rows = (36 * 1024) / (row_bytes * L.W);                         // tile budget
-  if (rows > kMaxSteps * lanes / L.W) rows = kMaxSteps * lanes / L.W;  // bounded per-thread partial sums
-  if (rows > L.H) rows = L.H;
-  if (rows < 1) {
-    if (size_t(row_bytes) * L.W > 96 * 1024) return fail(METRO_ERR_VALUE, "softargmax: one heatmap row (%d bytes) exceeds the tile budget", row_bytes * L.W);
-    rows = 1;
+  // tile: ~36 KB of whole rows, or an even part of one row when a row is larger than that (measured on
+  // B200: larger tiles amortise the per-tile bookkeeping better than more resident CTAs hide latency)
+  const int budget_px = (40 * 1024) / row_bytes;
+  int ppc;
+  if (budget_px >= L.W) {
+    int rows = budget_px / L.W;
+    if (rows > kMaxSteps * lanes / L.W) rows = kMaxSteps * lanes / L.W;   // bounded per-thread partial sums
+    if (rows > L.H) rows = L.H;
+    if (rows < 1) rows = 1;
+    ppc = rows * L.W;
+    L.tiles = (L.H + rows - 1) / rows;
+  } else {
+    int parts = 1;
+    while (L.W % (parts * 2) == 0 && (L.W / (parts * 2)) % lanes == 0 && L.W / parts > budget_px) parts *= 2;
+    ppc = L.W / parts;
+    if (size_t(ppc) * row_bytes > 90 * 1024) return fail(METRO_ERR_VALUE, "softargmax: a heatmap row of %d bytes cannot be tiled", row_bytes * L.W);
+    L.tiles = L.H * parts;
   }
-  L.ppc = rows * L.W;
-  L.tiles = (L.H + rows - 1) / rows;
-  // work items: one per crop unless the batch is too small to occupy the GPU, then a crop's tiles are
-  // split over several CTAs (merged by the last one to finish)
-  const int slots_gpu = 148 * 2;
-  int splits = d.splits > 0 ? d.splits : (n > 0 ? slots_gpu / n : 1);
+  L.ppc = ppc;
+  // work items: one per crop, or -- for large heatmaps -- a fixed number of row ranges per crop that
+  // depends on the heatmap shape ONLY, so a crop's result is bit-identical whatever batch or GPU shard it
+  // is part of (merged by the last CTA of the crop to finish)
+  int splits = d.splits > 0 ? d.splits : L.tiles / 8;
+  if (splits > 4 && d.splits <= 0) splits = 4;
   if (splits < 1) splits = 1;
   if (splits > L.tiles) splits = L.tiles;
   L.splits = splits;
@@ -408,22 +462,21 @@ size_t softargmax_workspace_bytes(const SoftargmaxLaunch &L) {
 
 metro_status softargmax_launch(const SoftargmaxLaunch &L, cudaStream_t stream) {
   if (L.n == 0) return METRO_OK;
-#define METRO_SAM(V, LN) return launch_t<V, LN>(L, stream)
-  if (L.head_f16) {
-    switch (L.lanes) {
-      case 1: METRO_SAM(8, 1);
-      case 2: METRO_SAM(8, 2);
-      case 4: METRO_SAM(8, 4);
-      case 8: METRO_SAM(8, 8);
-    }
-  } else {
-    switch (L.lanes) {
-      case 1: METRO_SAM(4, 1);
-      case 2: METRO_SAM(4, 2);
-      case 4: METRO_SAM(4, 4);
-      case 8: METRO_SAM(4, 8);
-    }
+  const int threads = (L.slots * L.lanes + 31) & ~31;
+#define METRO_SAM(V, LN, H) return (threads <= 192 ? launch_t<V, LN, H, 192>(L, stream) : launch_t<V, LN, H, kMaxThreads>(L, stream))
+#define METRO_SAM_LANES(V, H)        \
+  switch (L.lanes) {                 \
+    case 1: METRO_SAM(V, 1, H);      \
+    case 2: METRO_SAM(V, 2, H);      \
+    case 4: METRO_SAM(V, 4, H);      \
+    case 8: METRO_SAM(V, 8, H);      \
   }
+  if (L.head_f16) {
+    if (L.vec == 8) { METRO_SAM_LANES(8, true) } else { METRO_SAM_LANES(4, true) }
+  } else {
+    if (L.vec == 4) { METRO_SAM_LANES(4, false) } else { METRO_SAM_LANES(2, false) }
+  }
+#undef METRO_SAM_LANES
 #undef METRO_SAM
   return fail(METRO_ERR_INTERNAL, "softargmax: %d lanes not instantiated", L.lanes);
 }

@@ -171,13 +171,13 @@ class SoftArgmax:
 
     def __init__(self, side: int, n_joints_model: int, stride: int, permutation: Sequence[int], depth: int = 8,
                  centered_stride: bool = True, proc_side: int = 256, box_size_mm: float = 2200.0,
-                 head_dtype: str = 'f32', splits: int = 0, lanes: int = 0):
+                 head_dtype: str = 'f32', splits: int = 0, lanes: int = 0, word_bytes: int = 0):
         self.lib = _lib.load()
         self.perm = (C.c_int32 * len(permutation))(*permutation)
         self.n_out = len(permutation)
         self.desc = _lib.SoftargmaxDesc(side, n_joints_model, depth, stride, int(centered_stride), proc_side,
                                         box_size_mm, len(permutation), C.cast(self.perm, C.POINTER(C.c_int32)),
-                                        {'f32': 0, 'f16': 1}[head_dtype], splits, lanes)
+                                        {'f32': 0, 'f16': 1}[head_dtype], splits, lanes, word_bytes)
         self.side, self.channels = side, depth * n_joints_model
         self.head_dtype = head_dtype
         self._ws = None

@@ -39,7 +39,7 @@ class SoftargmaxDesc(C.Structure):
         ('side', C.c_int32), ('n_joints_model', C.c_int32), ('depth', C.c_int32), ('stride', C.c_int32),
         ('centered_stride', C.c_int32), ('proc_side', C.c_int32), ('box_size_mm', C.c_float),
         ('n_joints_out', C.c_int32), ('permutation', C.POINTER(C.c_int32)), ('head_dtype', C.c_int32),
-        ('splits', C.c_int32), ('lanes', C.c_int32),
+        ('splits', C.c_int32), ('lanes', C.c_int32), ('word_bytes', C.c_int32),
     ]
 
 

@@ -41,9 +41,9 @@ def stage_sam():
                 h = base.repeat((n + 7) // 8, 1, 1, 1)[:n].roll(r, 0).contiguous()
                 heads.append(h.half() if dt == 'f16' else h)
             P = side * side
-            for lanes, splits in [(0, 0), (2, 0), (4, 0), (8, 0), (4, 1), (4, 2), (4, 4), (8, 2), (2, 2)]:
+            for lanes, splits, wb in [(0, 0, 0), (2, 0, 8), (4, 0, 8), (2, 0, 16), (4, 1, 16), (4, 2, 16), (4, 4, 16), (4, 8, 16), (2, 2, 8), (2, 4, 8)]:
                 try:
-                    op = SoftArgmax(side, j, stride, perm, head_dtype=dt, splits=splits, lanes=lanes)
+                    op = SoftArgmax(side, j, stride, perm, head_dtype=dt, splits=splits, lanes=lanes, word_bytes=wb)
                     out = torch.empty((n, j, 3), device='cuda')
                     for r in range(nrot): op(heads[r], out)
                     torch.cuda.synchronize()
@@ -57,7 +57,7 @@ def stage_sam():
                     for _ in range(5): g.replay()
                     e1.record(); torch.cuda.synchronize()
                     us = e0.elapsed_time(e1) / (5 * it) * 1e3
-                    print(f'sam-time side={side} J={j} n={n} {dt} lanes={lanes} splits={splits}: {us:8.2f} us  {nbytes/us/1e3:8.1f} GB/s', flush=True)
+                    print(f'sam-time side={side} J={j} n={n} {dt} lanes={lanes} splits={splits} wb={wb}: {us:8.2f} us  {nbytes/us/1e3:8.1f} GB/s', flush=True)
                 except Exception as e:
                     print(f'sam-time side={side} J={j} {dt} lanes={lanes} splits={splits}: ERROR {e}', flush=True)
 
