@@ -31,8 +31,12 @@ namespace metro {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kCtrlWarps = 4;                 // 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle
+constexpr int kEpiWarps = 8;                  // two groups of four; group g drains accumulator stage g
+constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32;
 constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
+
+enum Mode { kSingle = 0, kDual = 1, kDirect = 2 };
 
 template <int BLOCK_N>
 struct Cfg {
@@ -47,9 +51,27 @@ struct Cfg {
 constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarTFull = 2 * kMaxStages, kBarTEmpty = kBarTFull + 2,
               kBarCount = kBarTEmpty + 2;
 
-template <int BLOCK_N, bool kDirect>
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// per-CTA role timers (cycles), written when p.prof != nullptr
+enum Prof { kPTotal = 0, kPProdWait, kPMmaWaitFull, kPMmaWaitAcc, kPEpiWaitAcc, kPEpiBusy, kPEpiWaitStore, kPTiles, kPCount };
+
+template <int BLOCK_N, int kMode>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BLOCK_N>;
+  constexpr int kParVecs = kMode == kDual ? 3 : 2;   // single/direct: scale, shift; dual: shift, scale2, shift2
   // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B).  The kernel has no
   // static shared memory, so the dynamic window starts at the CTA's shared base; verified below.
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -58,7 +80,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     __trap();
   }
   unsigned char *tiles = smem;
-  float *s_par = reinterpret_cast<float *>(smem + p.off_par);          // [4][BLOCK_N]
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
   uint64_t *full = bars + kBarFull, *empty = bars + kBarEmpty;
   uint64_t *tfull = bars + kBarTFull, *tempty = bars + kBarTEmpty;
@@ -71,19 +92,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int k0 = p.taps * p.cblk0;
   const int n_tiles_total = p.m_tiles * p.n_tiles;
   const int stages = p.stages;
+  const bool prof = p.prof != nullptr;
+  const long long t_start = prof ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.amap[0]);
     ptx::prefetch_tensormap(&p.bmap);
     if (p.cblk1) ptx::prefetch_tensormap(&p.a2map);
-    if (!kDirect) {
+    if (kMode != kDirect) {
       if (p.has_out1) ptx::prefetch_tensormap(&p.o1map);
       if (p.has_out2) ptx::prefetch_tensormap(&p.o2map);
     }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 128); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, kEpiWarps / 2); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -100,46 +123,73 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0;
+      auto acquire = [&]() -> unsigned char * {
+        if (prof) {
+          const long long t0 = clock64();
+          ptx::mbar_wait(empty + stage, phase ^ 1);
+          t_wait += clock64() - t0;
+        } else {
+          ptx::mbar_wait(empty + stage, phase ^ 1);
+        }
+        ptx::mbar_arrive_expect_tx(full + stage, C::kStageBytes);
+        return tiles + stage * C::kStageBytes;
+      };
+      auto advance = [&]() { if (++stage == stages) { stage = 0; phase ^= 1; } };
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
         int n0, h0;
         if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
         else { n0 = mt * p.nb; h0 = 0; }
-        const int cb2_0 = p.diag2 ? nt * (BLOCK_N / 64) : 0;
-        const int n_kb = k0 + (p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1);
-        for (int kb = 0; kb < n_kb; ++kb) {
-          ptx::mbar_wait(empty + stage, phase ^ 1);
-          unsigned char *sa = tiles + stage * C::kStageBytes;
-          unsigned char *sb = sa + C::kABytes;
-          ptx::mbar_arrive_expect_tx(full + stage, C::kStageBytes);
-          if (kb < k0) {
-            const int tap = kb / p.cblk0, cb = kb - tap * p.cblk0;
-            ptx::tma_load_4d(sa, &p.amap[p.tap_map[tap]], full + stage, cb * kTileK, p.tap_dw[tap],
-                             h0 + p.tap_dh[tap], n0);
-            ptx::tma_load_2d(sb, &p.bmap, full + stage, kb * kTileK, nt * BLOCK_N);
-          } else {
-            const int cb = cb2_0 + kb - k0;
-            ptx::tma_load_4d(sa, &p.a2map, full + stage, cb * kTileK, 0, h0, n0);
-            ptx::tma_load_2d(sb, &p.bmap, full + stage, (k0 + cb) * kTileK, nt * BLOCK_N);
+        const int ncol = nt * BLOCK_N;
+        int kcol = 0;                               // K coordinate in the packed weight matrix
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const CUtensorMap *am = &p.amap[p.tap_map[tap]];
+          const int dw = p.tap_dw[tap], hh = h0 + p.tap_dh[tap];
+          for (int cb = 0; cb < p.cblk0; ++cb, kcol += kTileK) {
+            unsigned char *sa = acquire();
+            ptx::tma_load_4d(sa, am, full + stage, cb * kTileK, dw, hh, n0);
+            ptx::tma_load_2d(sa + C::kABytes, &p.bmap, full + stage, kcol, ncol);
+            advance();
           }
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (p.cblk1) {
+          const int cb2_0 = p.diag2 ? nt * (BLOCK_N / 64) : 0;
+          const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
+          for (int cb = cb2_0; cb < cb2_0 + n2; ++cb) {
+            unsigned char *sa = acquire();
+            ptx::tma_load_4d(sa, &p.a2map, full + stage, cb * kTileK, 0, h0, n0);
+            ptx::tma_load_2d(sa + C::kABytes, &p.bmap, full + stage, (k0 + cb) * kTileK, ncol);
+            advance();
+          }
         }
       }
+      if (prof) p.prof[blockIdx.x * kPCount + kPProdWait] = t_wait;
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BLOCK_N);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      long long t_full = 0, t_acc = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
         const int nt = tile % p.n_tiles;
         const int n_kb = k0 + (p.diag2 ? min(BLOCK_N / 64, p.cblk1 - nt * (BLOCK_N / 64)) : p.cblk1);
-        ptx::mbar_wait(tempty + acc, aphase ^ 1);
+        const int acc = it & 1;
+        {
+          const long long t0 = prof ? clock64() : 0;
+          ptx::mbar_wait(tempty + acc, ((it >> 1) & 1) ^ 1);
+          if (prof) t_acc += clock64() - t0;
+        }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
         for (int kb = 0; kb < n_kb; ++kb) {
-          ptx::mbar_wait(full + stage, phase);
+          {
+            const long long t0 = prof ? clock64() : 0;
+            ptx::mbar_wait(full + stage, phase);
+            if (prof) t_full += clock64() - t0;
+          }
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(tiles + stage * C::kStageBytes);
           const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
@@ -152,57 +202,81 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           ptx::umma_commit(empty + stage);           // frees the smem slot when these MMAs retire
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(tfull + acc);               // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; aphase ^= 1; }
+        ptx::umma_commit(tfull + acc);               // accumulator complete -> epilogue group `acc`
+      }
+      if (prof) {
+        p.prof[blockIdx.x * kPCount + kPMmaWaitFull] = t_full;
+        p.prof[blockIdx.x * kPCount + kPMmaWaitAcc] = t_acc;
+        p.prof[blockIdx.x * kPCount + kPTiles] = it;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kCtrlWarps) {
     // ================================ epilogue ====================================
-    const int q = warp - 4;                          // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 128;                // 0..127 == accumulator row
-    int acc = 0;
-    uint32_t aphase = 0;
-    [[maybe_unused]] uint32_t chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+    // Group g = tiles with local index == g (mod 2) = accumulator stage g.  A warp owns the 32
+    // accumulator rows of its TMEM lane quarter: it converts them 32 columns at a time, stages the
+    // 32 x 32 fp16 box in its own 2 KB of shared memory (64-byte rows, 64B swizzle) and stores it
+    // with its own TMA store, so the eight warps never wait for each other inside a tile.
+    const int e = warp - kCtrlWarps, g = e >> 2, q = e & 3;   // q == warp % 4: the TMEM lane quarter
+    const int gt = threadIdx.x - (kCtrlWarps + 4 * g) * 32;   // 0..127 within the group
+    float *par = reinterpret_cast<float *>(smem + p.off_par) + g * kParVecs * BLOCK_N;
+    const uint32_t par_a = ptx::smem_u32(par);
+    const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + g * C::kAccCols;
+    const int n_st = (p.has_out1 ? 1 : 0) + (p.has_out2 ? 1 : 0);
+    const uint32_t st1 = ptx::smem_u32(smem + p.off_stage) + uint32_t(e * n_st) * 2048u;
+    const uint32_t st2 = st1 + (p.has_out1 ? 2048u : 0u);
+    const uint32_t row_a = uint32_t(lane) * 64u, sw = uint32_t(lane >> 1) & 3u;
+    int cur_nt = -1;
+    long long t_acc = 0, t_busy = 0, t_store = 0;
+    uint32_t k = 0;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < n_tiles_total; tile += 2 * gridDim.x, ++k) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int m0 = mt * kTileM;
-      // per-channel epilogue vectors of this N tile.  Every thread is past the last barrier of the
-      // previous tile, after which nobody reads s_par, so it can be overwritten right away; the
-      // first barrier below publishes it.
-      if constexpr (kDirect) ptx::named_bar_sync(1, 128);   // direct path has no trailing barrier
-      for (int i = et; i < BLOCK_N; i += 128) {
-        const int c = nt * BLOCK_N + i;
-        s_par[i] = p.scale[c];
-        s_par[BLOCK_N + i] = p.shift[c];
-        if (p.has_out2) { s_par[2 * BLOCK_N + i] = p.scale2[c]; s_par[3 * BLOCK_N + i] = p.shift2[c]; }
+      const int m0 = mt * kTileM + q * 32;
+      if (nt != cur_nt) {                            // per-channel epilogue vectors of this N tile
+        if (cur_nt >= 0) ptx::named_bar_sync(1 + g, 128);   // the group is done with the previous ones
+        for (int i = gt; i < BLOCK_N; i += 128) {
+          const int c = nt * BLOCK_N + i;
+          if (kMode == kDual) {
+            par[i] = p.shift[c]; par[BLOCK_N + i] = p.scale2[c]; par[2 * BLOCK_N + i] = p.shift2[c];
+          } else {
+            par[i] = p.scale[c]; par[BLOCK_N + i] = p.shift[c];
+          }
+        }
+        ptx::named_bar_sync(1 + g, 128);
+        cur_nt = nt;
       }
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * C::kAccCols;
+      long long t0 = prof ? clock64() : 0;
+      ptx::mbar_wait(tfull + g, k & 1);
+      ptx::tc_fence_after();
+      long long t1 = prof ? clock64() : 0;
+      t_acc += t1 - t0;
 
-      if constexpr (kDirect) {
-        // ---- fp32 direct-store path (logits head: few columns, masked tail) ----
-        ptx::named_bar_sync(1, 128);
-        const int m = m0 + et;
+      if constexpr (kMode == kDirect) {
+        // ---- direct-store path (logits head: few columns, masked tail; fp32 or fp16) ----
+        const int m = m0 + lane;
         const bool valid = m < p.m_total;
-        ptx::mbar_wait(tfull + acc, aphase);
-        ptx::tc_fence_after();
 #pragma unroll 1
         for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
           const int col0 = nt * BLOCK_N + chunk * 32;
           if (col0 >= p.cout) break;                 // uniform: padded head columns
           uint32_t v[32];
           __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
-          ptx::tmem_ld_32x32(taddr + chunk * 32, v);
+          ptx::tmem_ld_32x32(taddr0 + chunk * 32, v);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + 8 * g;
+          for (int j = 0; j < 4; ++j) {
+            const int col = col0 + 8 * j;
             if (col >= p.cout) break;                // uniform (cout is a multiple of 8)
+            const uint32_t pa = par_a + uint32_t(chunk * 32 + 8 * j) * 4u;
+            const float4 s0 = ptx::lds_v4(pa), s1 = ptx::lds_v4(pa + 16);
+            const float4 b0 = ptx::lds_v4(pa + BLOCK_N * 4), b1 = ptx::lds_v4(pa + BLOCK_N * 4 + 16);
             float f[8];
+            f[0] = fmaf(__uint_as_float(v[8 * j + 0]), s0.x, b0.x); f[1] = fmaf(__uint_as_float(v[8 * j + 1]), s0.y, b0.y);
+            f[2] = fmaf(__uint_as_float(v[8 * j + 2]), s0.z, b0.z); f[3] = fmaf(__uint_as_float(v[8 * j + 3]), s0.w, b0.w);
+            f[4] = fmaf(__uint_as_float(v[8 * j + 4]), s1.x, b1.x); f[5] = fmaf(__uint_as_float(v[8 * j + 5]), s1.y, b1.y);
+            f[6] = fmaf(__uint_as_float(v[8 * j + 6]), s1.z, b1.z); f[7] = fmaf(__uint_as_float(v[8 * j + 7]), s1.w, b1.w);
+            if (p.relu1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int pi = chunk * 32 + 8 * g + i;
-              f[i] = fmaf(__uint_as_float(v[8 * g + i]), s_par[pi], s_par[BLOCK_N + pi]);
-              if (p.relu1) f[i] = fmaxf(f[i], 0.f);
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (valid) {
               const size_t off = size_t(m) * p.cout + col;
@@ -212,91 +286,104 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 dst[1] = make_float4(f[4], f[5], f[6], f[7]);
               } else {
                 uint4 o;
-                __half2 *oh2 = reinterpret_cast<__half2 *>(&o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) oh2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                o.x = pack_f16x2(f[0], f[1]); o.y = pack_f16x2(f[2], f[3]);
+                o.z = pack_f16x2(f[4], f[5]); o.w = pack_f16x2(f[6], f[7]);
                 *reinterpret_cast<uint4 *>(static_cast<__half *>(p.out1) + off) = o;
               }
             }
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty + g);
       } else {
-        // ---- fp16 path: TMEM -> registers -> swizzled smem chunk (128 rows x 64 cols) -> TMA store.
+        // ---- fp16 path: TMEM -> registers -> swizzled 32x32 box in smem -> TMA store.
         //      (The identity-shortcut residual is not an epilogue operand: it is accumulated by the
         //      tensor core as extra K blocks against identity weights, see the producer.) ----
-        constexpr int kChunks = BLOCK_N / 64;
-        const uint32_t sw = uint32_t(et & 7);
-        const uint32_t row_off = uint32_t(et) * 128;
-        bool waited = false;
+        constexpr int kChunks = BLOCK_N / 32;
 #pragma unroll 1
-        for (int c = 0; c < kChunks; ++c, ++chunk_ctr) {
-          const int ob = (p.obufs == 2) ? int(chunk_ctr & 1) : 0;
-          if (et == 0) {      // the store that last used staging buffer `ob` must have drained it
-            if (p.obufs == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
-          }
-          ptx::named_bar_sync(1, 128);
-          if (!waited) {
-            ptx::mbar_wait(tfull + acc, aphase);
-            ptx::tc_fence_after();
-            waited = true;
-          }
-          unsigned char *so1 = smem + p.off_out1 + ob * kChunkBytes;
-          unsigned char *so2 = smem + p.off_out2 + ob * kChunkBytes;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t v[32];
+          __syncwarp();
+          ptx::tmem_ld_32x32(taddr0 + c * 32, v);
+          ptx::tmem_ld_wait();
+          if (c == kChunks - 1) {                    // accumulator drained: hand the stage back early
+            ptx::tc_fence_before();
             __syncwarp();
-            ptx::tmem_ld_32x32(taddr + c * 64 + half * 32, v);
-            ptx::tmem_ld_wait();
+            if (lane == 0) ptx::mbar_arrive(tempty + g);
+          }
+          uint4 o1[4], o2[4];
+          const uint32_t pa = par_a + uint32_t(c * 32) * 4u;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int j = half * 4 + g;                       // 16-byte chunk within the 128-byte row
-              const uint32_t soff = row_off + ((uint32_t(j) ^ sw) << 4);
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int pi = c * 64 + j * 8 + i;
-                f[i] = fmaf(__uint_as_float(v[8 * g + i]), s_par[pi], s_par[BLOCK_N + pi]);
-              }
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t pj = pa + uint32_t(j) * 32u;
+            uint32_t *w1 = reinterpret_cast<uint32_t *>(&o1[j]);
+            uint32_t *w2 = reinterpret_cast<uint32_t *>(&o2[j]);
+            if constexpr (kMode == kSingle) {
+              const float4 s0 = ptx::lds_v4(pj), s1 = ptx::lds_v4(pj + 16);
+              const float4 b0 = ptx::lds_v4(pj + BLOCK_N * 4), b1 = ptx::lds_v4(pj + BLOCK_N * 4 + 16);
+              const float2 y0 = __ffma2_rn(make_float2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])), make_float2(s0.x, s0.y), make_float2(b0.x, b0.y));
+              const float2 y1 = __ffma2_rn(make_float2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])), make_float2(s0.z, s0.w), make_float2(b0.z, b0.w));
+              const float2 y2 = __ffma2_rn(make_float2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])), make_float2(s1.x, s1.y), make_float2(b1.x, b1.y));
+              const float2 y3 = __ffma2_rn(make_float2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])), make_float2(s1.z, s1.w), make_float2(b1.z, b1.w));
               if (p.relu1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+                w1[0] = pack_relu_f16x2(y0.x, y0.y); w1[1] = pack_relu_f16x2(y1.x, y1.y);
+                w1[2] = pack_relu_f16x2(y2.x, y2.y); w1[3] = pack_relu_f16x2(y3.x, y3.y);
+              } else {
+                w1[0] = pack_f16x2(y0.x, y0.y); w1[1] = pack_f16x2(y1.x, y1.y);
+                w1[2] = pack_f16x2(y2.x, y2.y); w1[3] = pack_f16x2(y3.x, y3.y);
               }
-              uint4 o;
-              __half2 *oh2 = reinterpret_cast<__half2 *>(&o);
+            } else {
+              // y = acc + bias (raw sum, stored as fp16); y2 = relu(fp16(y) * scale2 + shift2): the next
+              // unit's pre-activation computed from the fp16 value its consumer would have read
+              const float4 b0 = ptx::lds_v4(pj), b1 = ptx::lds_v4(pj + 16);
+              const float4 s0 = ptx::lds_v4(pj + BLOCK_N * 4), s1 = ptx::lds_v4(pj + BLOCK_N * 4 + 16);
+              const float4 f0 = ptx::lds_v4(pj + BLOCK_N * 8), f1 = ptx::lds_v4(pj + BLOCK_N * 8 + 16);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float ff[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) oh2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-              if (p.has_out1) *reinterpret_cast<uint4 *>(so1 + soff) = o;
-              if (p.has_out2) {
-                uint4 o2;
-                __half2 *o2h = reinterpret_cast<__half2 *>(&o2);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int pi = c * 64 + j * 8 + 2 * i;
-                  const float2 y = __half22float2(oh2[i]);     // the fp16 value the consumer would read
-                  const float a = fmaxf(fmaf(y.x, s_par[2 * BLOCK_N + pi], s_par[3 * BLOCK_N + pi]), 0.f);
-                  const float b = fmaxf(fmaf(y.y, s_par[2 * BLOCK_N + pi + 1], s_par[3 * BLOCK_N + pi + 1]), 0.f);
-                  o2h[i] = __floats2half2_rn(a, b);
-                }
-                *reinterpret_cast<uint4 *>(so2 + soff) = o2;
+              for (int i = 0; i < 4; ++i) {
+                const float2 y = __fadd2_rn(make_float2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1])),
+                                            make_float2(bb[2 * i], bb[2 * i + 1]));
+                w1[i] = pack_f16x2(y.x, y.y);
+                const float2 yh = __half22float2(*reinterpret_cast<const __half2 *>(&w1[i]));
+                const float2 z = __ffma2_rn(yh, make_float2(ss[2 * i], ss[2 * i + 1]), make_float2(ff[2 * i], ff[2 * i + 1]));
+                w2[i] = pack_relu_f16x2(z.x, z.y);
               }
             }
           }
+          // the previous store from this warp's staging buffers must have finished reading them
+          {
+            const long long s0 = prof ? clock64() : 0;
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+            if (prof) t_store += clock64() - s0;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t soff = row_a + ((uint32_t(j) ^ sw) << 4);
+            if (kMode == kSingle || p.has_out1) sts_v4(st1 + soff, o1[j]);
+            if (kMode == kDual) sts_v4(st2 + soff, o2[j]);
+          }
           ptx::fence_proxy_async();                  // generic-proxy smem writes -> visible to TMA
-          ptx::named_bar_sync(1, 128);
-          if (et == 0) {
-            const int col0 = nt * BLOCK_N + c * 64;
-            if (p.has_out1) ptx::tma_store_2d(&p.o1map, so1, col0, m0);
-            if (p.has_out2) ptx::tma_store_2d(&p.o2map, so2, col0, m0);
+          __syncwarp();
+          if (lane == 0) {
+            const int col0 = nt * BLOCK_N + c * 32;
+            if (kMode == kSingle || p.has_out1) ptx::tma_store_2d_a(&p.o1map, st1, col0, m0);
+            if (kMode == kDual) ptx::tma_store_2d_a(&p.o2map, st2, col0, m0);
             ptx::bulk_commit();
           }
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty + acc);
-      if (++acc == 2) { acc = 0; aphase ^= 1; }
+      if (prof) t_busy += clock64() - t1;
     }
-    if (!kDirect && et == 0) ptx::bulk_wait<0>();    // smem must outlive the last TMA store
+    if (kMode != kDirect && lane == 0) ptx::bulk_wait<0>();    // smem must outlive the last TMA store
+    if (prof && e == 0 && lane == 0) {
+      p.prof[blockIdx.x * kPCount + kPEpiWaitAcc] = t_acc;
+      p.prof[blockIdx.x * kPCount + kPEpiBusy] = t_busy;
+      p.prof[blockIdx.x * kPCount + kPEpiWaitStore] = t_store;
+    }
   }
 
   ptx::tc_fence_before();
@@ -305,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
+  if (prof && threadIdx.x == 0) p.prof[blockIdx.x * kPCount + kPTotal] = clock64() - t_start;
 }
 
 // ---- driver entry point -------------------------------------------------------------------------------
@@ -324,18 +412,18 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-template <int BLOCK_N, bool kDirect>
+template <int BLOCK_N, int kMode>
 metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
-  static int configured = 0;
-  if (configured < L.prm.smem_bytes) {
-    METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static bool configured = false;
+  if (!configured) {
+    METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemLimit));
-    configured = kSmemLimit;
+    configured = true;
   }
   const int tiles = L.prm.m_tiles * L.prm.n_tiles;
   if (tiles == 0) return METRO_OK;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  conv_gemm_kernel<BLOCK_N, kDirect><<<grid, kThreads, L.prm.smem_bytes, stream>>>(L.prm);
+  conv_gemm_kernel<BLOCK_N, kMode><<<grid, kThreads, L.prm.smem_bytes, stream>>>(L.prm);
   METRO_CUDA(cudaGetLastError());
   return METRO_OK;
 }
@@ -365,10 +453,10 @@ metro_status make_out_tensor_map(CUtensorMap *map, const void *base, long long m
   if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[2] = {cuuint64_t(cout), cuuint64_t(m_rows)};
   const cuuint64_t strides[1] = {cuuint64_t(cout) * 2};
-  const cuuint32_t box[2] = {64, cuuint32_t(kTileM)};
+  const cuuint32_t box[2] = {32, 32};   // one epilogue warp's box: 32 columns (64 B) x 32 rows
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled(output rows=%lld cout=%d) -> %d", m_rows, cout, int(r));
@@ -418,22 +506,19 @@ int conv_gemm_pick_block_n(int cout, bool direct) {
 }
 
 metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks) {
+  (void)k_blocks;
   ConvGemmParams &p = L.prm;
   const int stage_bytes = kTileM * kTileK * 2 + L.block_n * kTileK * 2;
-  const int fixed = 4 * L.block_n * 4 + 256;       // epilogue vectors + barrier block
   const int n_out = L.direct ? 0 : (p.has_out1 ? 1 : 0) + (p.has_out2 ? 1 : 0);
-  auto stages_for = [&](int obufs) { return (kSmemLimit - fixed - n_out * obufs * kChunkBytes) / stage_bytes; };
-  // double-buffered staging unless a long K loop would rather have one more pipeline stage
-  p.obufs = 2;
-  if (n_out && k_blocks >= 8 && stages_for(2) < 4 && stages_for(1) >= 4) p.obufs = 1;
-  int stages = stages_for(p.obufs);
-  if (stages > 6) stages = 6;
+  const int par_bytes = 2 * (p.has_out2 ? 3 : 2) * L.block_n * 4;     // two epilogue groups
+  const int stage_out = kEpilogueWarps * n_out * kWarpStageBytes;
+  int stages = (kSmemLimit - 256 - par_bytes - stage_out) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(METRO_ERR_INTERNAL, "conv_gemm: shared memory plan leaves %d stages", stages);
   p.stages = stages;
   int off = stages * stage_bytes;
-  p.off_out1 = off; off += (p.has_out1 && !L.direct ? p.obufs : 0) * kChunkBytes;
-  p.off_out2 = off; off += (p.has_out2 ? p.obufs : 0) * kChunkBytes;
-  p.off_par = off; off += 4 * L.block_n * 4;
+  p.off_stage = off; off += stage_out;
+  p.off_par = off; off += par_bytes;
   p.off_bar = off; off += 256;
   p.smem_bytes = off;
   return METRO_OK;
@@ -501,13 +586,25 @@ void conv_gemm_pack_weights(const float *w, int k, int cin, int cout, const floa
 }
 
 metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
-  switch (L.block_n) {
-    case 64: return launch_t<64, false>(L, num_sms, stream);
-    case 128: return launch_t<128, false>(L, num_sms, stream);
-    case 160: return launch_t<160, true>(L, num_sms, stream);
-    case 256: return L.direct ? launch_t<256, true>(L, num_sms, stream) : launch_t<256, false>(L, num_sms, stream);
-    default: return fail(METRO_ERR_INTERNAL, "conv_gemm: unsupported BLOCK_N %d", L.block_n);
+  if (L.direct) {
+    switch (L.block_n) {
+      case 160: return launch_t<160, kDirect>(L, num_sms, stream);
+      case 256: return launch_t<256, kDirect>(L, num_sms, stream);
+    }
+  } else if (L.prm.has_out2) {
+    switch (L.block_n) {
+      case 64: return launch_t<64, kDual>(L, num_sms, stream);
+      case 128: return launch_t<128, kDual>(L, num_sms, stream);
+      case 256: return launch_t<256, kDual>(L, num_sms, stream);
+    }
+  } else {
+    switch (L.block_n) {
+      case 64: return launch_t<64, kSingle>(L, num_sms, stream);
+      case 128: return launch_t<128, kSingle>(L, num_sms, stream);
+      case 256: return launch_t<256, kSingle>(L, num_sms, stream);
+    }
   }
+  return fail(METRO_ERR_INTERNAL, "conv_gemm: unsupported BLOCK_N %d", L.block_n);
 }
 
 }  // namespace metro

@@ -14,7 +14,8 @@ constexpr int kTileM = 128;     // output pixels per tile (UMMA M)
 constexpr int kTileK = 64;      // fp16 channels per K block = one 128-byte swizzle row
 constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 8;
-constexpr int kChunkBytes = kTileM * 128;   // one 128-row x 64-column fp16 staging chunk (16 KB)
+constexpr int kWarpStageBytes = 32 * 64;    // one epilogue warp's staging box: 32 rows x 32 fp16 columns (2 KB)
+constexpr int kEpilogueWarps = 8;
 
 // Kernel parameters (passed by value as a __grid_constant__; tensor maps must be 64-byte aligned).
 struct alignas(64) ConvGemmParams {
@@ -37,8 +38,9 @@ struct alignas(64) ConvGemmParams {
   int out1_f32;
   int has_out1, has_out2, relu1;
   // shared-memory plan (bytes from the 1024-aligned base)
-  int stages, obufs;
-  int off_out1, off_out2, off_par, off_bar, smem_bytes;
+  int stages;
+  int off_stage, off_par, off_bar, smem_bytes;
+  long long *prof;       // optional [grid][8] per-CTA role timers (cycles); nullptr = off
 };
 
 struct ConvGemmLaunch {

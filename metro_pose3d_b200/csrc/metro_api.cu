@@ -417,6 +417,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
 struct Timer {
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> names;
+  long long *role_prof = nullptr;   // device [launch][num_sms][8] role timers (METRO_ROLE_PROF=1)
 };
 
 metro_status run(metro_handle *h, const void *images, bool u8, int n, float *poses, cudaStream_t s, Timer *t) {
@@ -436,13 +437,17 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
   if ((st = s2d_pack_launch(images, u8, h->buf_s2d, n, pl.proc_side, h->s2d_hp, h->s2d_wp, h->s2d_win, s)) != METRO_OK) return st;
   mark("s2d_pack");
   conv_gemm_set_batch(h->root_gemm.prm, n);
+  h->root_gemm.prm.prof = (t && t->role_prof) ? t->role_prof : nullptr;
   if ((st = conv_gemm_launch(h->root_gemm, h->num_sms, s)) != METRO_OK) return st;
   mark("conv1");
   if ((st = pool_preact_launch(h->buf_root, h->pool_raw, h->pool_pre, h->d_pool_scale, h->d_pool_shift, n, pl.pool_in,
                                pl.pool_out, 64, s)) != METRO_OK) return st;
   mark("pool1");
+  int li = 1;
   for (auto &L : h->gemms) {
     conv_gemm_set_batch(L.prm, n);
+    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li) * h->num_sms * 8 : nullptr;
+    ++li;
     if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
@@ -663,10 +668,41 @@ metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launc
 metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev, float *ms_out,
                            char *names_buf, size_t names_bytes, int32_t *n_launches) {
   Timer t;
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  const bool roles = getenv("METRO_ROLE_PROF") != nullptr;
+  const size_t role_elems = size_t(h->gemms.size() + 1) * h->num_sms * 8;
+  if (roles) {
+    METRO_CUDA(cudaMalloc(&t.role_prof, role_elems * sizeof(long long)));
+    METRO_CUDA(cudaMemset(t.role_prof, 0, role_elems * sizeof(long long)));
+  }
   METRO_CUDA(cudaDeviceSynchronize());
   metro_status st = run(h, images_dev, false, n, poses_dev, nullptr, &t);
   if (st != METRO_OK) return st;
   METRO_CUDA(cudaDeviceSynchronize());
+  if (roles) {
+    // per launch, averaged over CTAs: total | producer waits for a free stage | MMA waits for operands |
+    // MMA waits for a free accumulator | epilogue waits for an accumulator | epilogue busy | store wait | tiles
+    std::vector<long long> host(role_elems);
+    METRO_CUDA(cudaMemcpy(host.data(), t.role_prof, role_elems * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(t.role_prof);
+    fprintf(stderr, "%-28s %9s %9s %9s %9s %9s %9s %9s %6s\n", "roles (kcycles, CTA mean)", "total", "prod_wait", "mma_full",
+            "mma_acc", "epi_wait", "epi_busy", "st_wait", "tiles");
+    for (size_t l = 0; l <= h->gemms.size(); ++l) {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int ctas = 0;
+      for (int c = 0; c < h->num_sms; ++c) {
+        const long long *r = &host[(l * h->num_sms + c) * 8];
+        if (r[0] == 0) continue;
+        ++ctas;
+        for (int k = 0; k < 8; ++k) acc[k] += double(r[k]);
+      }
+      if (!ctas) continue;
+      const std::string &nm = l == 0 ? h->root_gemm.name : h->gemms[l - 1].name;
+      fprintf(stderr, "%-28s %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %6.1f\n", nm.c_str(), acc[0] / ctas / 1e3,
+              acc[1] / ctas / 1e3, acc[2] / ctas / 1e3, acc[3] / ctas / 1e3, acc[4] / ctas / 1e3, acc[5] / ctas / 1e3,
+              acc[6] / ctas / 1e3, acc[7] / ctas);
+    }
+  }
   std::string names;
   const int cnt = int(t.ev.size()) - 1;
   for (int i = 0; i < cnt; ++i) {

@@ -41,6 +41,6 @@ if __name__ == '__main__':
     elif what == 'sam_e':
         sam(64, 4, 19, 128)
     elif what == 'net':
-        net()
+        net(n=int(sys.argv[2]) if len(sys.argv) > 2 else 256, steps=int(sys.argv[3]) if len(sys.argv) > 3 else 2)
     elif what == 'net_d':
         net('resnet_v2_101', 16, 'coco19')
