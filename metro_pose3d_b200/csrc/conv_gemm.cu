@@ -40,8 +40,8 @@ enum Mode { kSingle = 0, kDual = 1, kDirect = 2 };
 
 template <int BLOCK_N>
 struct Cfg {
-  static constexpr int kABytes = kTileM * kTileK * 2;          // 16 KB
-  static constexpr int kBBytes = BLOCK_N * kTileK * 2;
+  static constexpr int kABytes = kTileM * kTileK * 2;          // 16 KB: this CTA's 128 pixel rows
+  static constexpr int kBBytes = (BLOCK_N / 2) * kTileK * 2;   // this CTA's half of the weight rows
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAccCols = BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256);  // per accumulator stage
   static constexpr int kTmemCols = 2 * kAccCols;               // power of two >= 32
@@ -66,10 +66,17 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
 }
 
 // per-CTA role timers (cycles), written when p.prof != nullptr
-enum Prof { kPTotal = 0, kPProdWait, kPMmaWaitFull, kPMmaWaitAcc, kPEpiWaitAcc, kPEpiBusy, kPEpiWaitStore, kPTiles, kPCount };
+enum Prof { kPTotal = 0, kPProdWait, kPMmaWaitFull, kPMmaWaitAcc, kPEpiWaitAcc, kPEpiBusy, kPEpiWaitStore, kPTiles,
+            kPEpiLd, kPEpiMath, kPEpiSts, kPEpiIssue, kPEpiPar, kPMmaIssue, kPMmaCommit, kPProdIssue, kPCount = 16 };
 
+// The kernel runs as CTA pairs (cluster of 2 = one TPC, tcgen05 cta_group::2): a pair owns a tile of
+// 256 output pixels x BLOCK_N channels.  Each CTA stages its own 128 pixel rows of A and HALF of the
+// weight rows per K block (so a stage is 16 KB + BLOCK_N/2 x 128 B and shared-memory write + read
+// traffic per MMA halves against a one-CTA tile), the leader's elected thread issues one M=256 MMA
+// for both tensor cores, and each CTA drains its own 128 accumulator rows from its own TMEM.
 template <int BLOCK_N, int kMode>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BLOCK_N>;
   constexpr int kParVecs = kMode == kDual ? 3 : 2;   // single/direct: scale, shift; dual: shift, scale2, shift2
   // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B).  The kernel has no
@@ -90,7 +97,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   // shortcut) or, for the identity shortcut (diag2), only the BLOCK_N/64 blocks whose identity
   // weights hit this N tile.
   const int k0 = p.taps * p.cblk0;
-  const int n_tiles_total = p.m_tiles * p.n_tiles;
+  const uint32_t rank = ptx::cluster_ctarank();     // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_tiles_total = ((p.m_tiles + 1) >> 1) * p.n_tiles;   // pair tiles
   const int stages = p.stages;
   const bool prof = p.prof != nullptr;
   const long long t_start = prof ? clock64() : 0;
@@ -106,15 +115,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, kEpiWarps / 2); }
+    // tempty (the leader's is the one used): the four warps of the group in BOTH CTAs
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, kEpiWarps); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(s_tmem, C::kTmemCols);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_pair(s_tmem, C::kTmemCols);
+    ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  ptx::cluster_sync();                               // both CTAs' barriers exist before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
@@ -123,7 +134,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      long long t_wait = 0;
+      long long t_wait = 0, t_issue = 0;
+      // operands of both CTAs land on the LEADER's full barrier (it alone arms the byte count)
+      const uint32_t full0 = ptx::mapa(ptx::smem_u32(full), 0);
       auto acquire = [&]() -> unsigned char * {
         if (prof) {
           const long long t0 = clock64();
@@ -132,25 +145,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         } else {
           ptx::mbar_wait(empty + stage, phase ^ 1);
         }
-        ptx::mbar_arrive_expect_tx(full + stage, C::kStageBytes);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(full + stage, 2 * C::kStageBytes);
         return tiles + stage * C::kStageBytes;
       };
       auto advance = [&]() { if (++stage == stages) { stage = 0; phase ^= 1; } };
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      for (int tile = pair; tile < n_tiles_total; tile += n_pairs) {
+        const int mp = tile / p.n_tiles, nt = tile - mp * p.n_tiles;
+        const int mt = 2 * mp + int(rank);          // this CTA's 128-pixel tile (may be one past the end: zero fill)
         int n0, h0;
         if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
         else { n0 = mt * p.nb; h0 = 0; }
-        const int ncol = nt * BLOCK_N;
+        const int ncol = nt * BLOCK_N + int(rank) * (BLOCK_N / 2);   // this CTA's half of the weight rows
         int kcol = 0;                               // K coordinate in the packed weight matrix
         for (int tap = 0; tap < p.taps; ++tap) {
           const CUtensorMap *am = &p.amap[p.tap_map[tap]];
           const int dw = p.tap_dw[tap], hh = h0 + p.tap_dh[tap];
           for (int cb = 0; cb < p.cblk0; ++cb, kcol += kTileK) {
             unsigned char *sa = acquire();
-            ptx::tma_load_4d(sa, am, full + stage, cb * kTileK, dw, hh, n0);
-            ptx::tma_load_2d(sa + C::kABytes, &p.bmap, full + stage, kcol, ncol);
+            const long long i0 = prof ? clock64() : 0;
+            const uint32_t fb = full0 + uint32_t(stage) * 8u;
+            ptx::tma_load_4d_pair(sa, am, fb, cb * kTileK, dw, hh, n0);
+            ptx::tma_load_2d_pair(sa + C::kABytes, &p.bmap, fb, kcol, ncol);
             advance();
+            if (prof) t_issue += clock64() - i0;
           }
         }
         if (p.cblk1) {
@@ -158,22 +175,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
           for (int cb = cb2_0; cb < cb2_0 + n2; ++cb) {
             unsigned char *sa = acquire();
-            ptx::tma_load_4d(sa, &p.a2map, full + stage, cb * kTileK, 0, h0, n0);
-            ptx::tma_load_2d(sa + C::kABytes, &p.bmap, full + stage, (k0 + cb) * kTileK, ncol);
+            const uint32_t fb = full0 + uint32_t(stage) * 8u;
+            ptx::tma_load_4d_pair(sa, &p.a2map, fb, cb * kTileK, 0, h0, n0);
+            ptx::tma_load_2d_pair(sa + C::kABytes, &p.bmap, fb, (k0 + cb) * kTileK, ncol);
             advance();
           }
         }
       }
-      if (prof) p.prof[blockIdx.x * kPCount + kPProdWait] = t_wait;
+      if (prof) { p.prof[blockIdx.x * kPCount + kPProdWait] = t_wait; p.prof[blockIdx.x * kPCount + kPProdIssue] = t_issue; }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BLOCK_N);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kTileM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0, it = 0;
-      long long t_full = 0, t_acc = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+      long long t_full = 0, t_acc = 0, t_mi = 0, t_mc = 0;
+      for (int tile = pair; tile < n_tiles_total; tile += n_pairs, ++it) {
         const int nt = tile % p.n_tiles;
         const int n_kb = k0 + (p.diag2 ? min(BLOCK_N / 64, p.cblk1 - nt * (BLOCK_N / 64)) : p.cblk1);
         const int acc = it & 1;
@@ -191,23 +209,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (prof) t_full += clock64() - t0;
           }
           ptx::tc_fence_after();
+          const long long m0 = prof ? clock64() : 0;
           const uint32_t sa = ptx::smem_u32(tiles + stage * C::kStageBytes);
           const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
           const uint64_t db = ptx::make_sw128_kmajor_desc(sa + C::kABytes);
 #pragma unroll
           for (int k = 0; k < kTileK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          ptx::umma_commit(empty + stage);           // frees the smem slot when these MMAs retire
+          const long long m1 = prof ? clock64() : 0;
+          ptx::umma_commit_pair(empty + stage, 3);   // frees the smem slot in both CTAs when these MMAs retire
           if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (prof) { t_mi += m1 - m0; t_mc += clock64() - m1; }
         }
-        ptx::umma_commit(tfull + acc);               // accumulator complete -> epilogue group `acc`
+        ptx::umma_commit_pair(tfull + acc, 3);       // accumulator complete -> epilogue group `acc` of both CTAs
       }
       if (prof) {
         p.prof[blockIdx.x * kPCount + kPMmaWaitFull] = t_full;
         p.prof[blockIdx.x * kPCount + kPMmaWaitAcc] = t_acc;
         p.prof[blockIdx.x * kPCount + kPTiles] = it;
+        p.prof[blockIdx.x * kPCount + kPMmaIssue] = t_mi;
+        p.prof[blockIdx.x * kPCount + kPMmaCommit] = t_mc;
       }
     }
   } else if (warp >= kCtrlWarps) {
@@ -225,12 +248,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t st1 = ptx::smem_u32(smem + p.off_stage) + uint32_t(e * n_st) * 2048u;
     const uint32_t st2 = st1 + (p.has_out1 ? 2048u : 0u);
     const uint32_t row_a = uint32_t(lane) * 64u, sw = uint32_t(lane >> 1) & 3u;
+    const uint32_t tempty0 = ptx::mapa(ptx::smem_u32(tempty + g), 0);   // the leader's barrier
     int cur_nt = -1;
-    long long t_acc = 0, t_busy = 0, t_store = 0;
+    long long t_acc = 0, t_busy = 0, t_store = 0, t_ld = 0, t_math = 0, t_sts = 0, t_issue = 0, t_par = 0;
     uint32_t k = 0;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < n_tiles_total; tile += 2 * gridDim.x, ++k) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int m0 = mt * kTileM + q * 32;
+    for (int tile = pair + g * n_pairs; tile < n_tiles_total; tile += 2 * n_pairs, ++k) {
+      const int mp = tile / p.n_tiles, nt = tile - mp * p.n_tiles;
+      const int m0 = (2 * mp + int(rank)) * kTileM + q * 32;
+      const long long tp0 = prof ? clock64() : 0;
       if (nt != cur_nt) {                            // per-channel epilogue vectors of this N tile
         if (cur_nt >= 0) ptx::named_bar_sync(1 + g, 128);   // the group is done with the previous ones
         for (int i = gt; i < BLOCK_N; i += 128) {
@@ -245,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         cur_nt = nt;
       }
       long long t0 = prof ? clock64() : 0;
+      t_par += t0 - tp0;
       ptx::mbar_wait(tfull + g, k & 1);
       ptx::tc_fence_after();
       long long t1 = prof ? clock64() : 0;
@@ -295,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty + g);
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty0);
       } else {
         // ---- fp16 path: TMEM -> registers -> swizzled 32x32 box in smem -> TMA store.
         //      (The identity-shortcut residual is not an epilogue operand: it is accumulated by the
@@ -304,13 +330,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
           uint32_t v[32];
+          const long long c0 = prof ? clock64() : 0;
           __syncwarp();
           ptx::tmem_ld_32x32(taddr0 + c * 32, v);
           ptx::tmem_ld_wait();
+          const long long c1 = prof ? clock64() : 0;
           if (c == kChunks - 1) {                    // accumulator drained: hand the stage back early
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty + g);
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty0);
           }
           uint4 o1[4], o2[4];
           const uint32_t pa = par_a + uint32_t(c * 32) * 4u;
@@ -354,12 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
           // the previous store from this warp's staging buffers must have finished reading them
-          {
-            const long long s0 = prof ? clock64() : 0;
-            if (lane == 0) ptx::bulk_wait_read<0>();
-            __syncwarp();
-            if (prof) t_store += clock64() - s0;
-          }
+          const long long c2 = prof ? clock64() : 0;
+          if (lane == 0) ptx::bulk_wait_read<0>();
+          __syncwarp();
+          const long long c3 = prof ? clock64() : 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t soff = row_a + ((uint32_t(j) ^ sw) << 4);
@@ -368,11 +394,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           ptx::fence_proxy_async();                  // generic-proxy smem writes -> visible to TMA
           __syncwarp();
+          const long long c4 = prof ? clock64() : 0;
           if (lane == 0) {
             const int col0 = nt * BLOCK_N + c * 32;
             if (kMode == kSingle || p.has_out1) ptx::tma_store_2d_a(&p.o1map, st1, col0, m0);
             if (kMode == kDual) ptx::tma_store_2d_a(&p.o2map, st2, col0, m0);
             ptx::bulk_commit();
+          }
+          if (prof) {
+            t_ld += c1 - c0; t_math += c2 - c1; t_store += c3 - c2; t_sts += c4 - c3; t_issue += clock64() - c4;
           }
         }
       }
@@ -383,14 +413,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       p.prof[blockIdx.x * kPCount + kPEpiWaitAcc] = t_acc;
       p.prof[blockIdx.x * kPCount + kPEpiBusy] = t_busy;
       p.prof[blockIdx.x * kPCount + kPEpiWaitStore] = t_store;
+      p.prof[blockIdx.x * kPCount + kPEpiLd] = t_ld;
+      p.prof[blockIdx.x * kPCount + kPEpiMath] = t_math;
+      p.prof[blockIdx.x * kPCount + kPEpiSts] = t_sts;
+      p.prof[blockIdx.x * kPCount + kPEpiIssue] = t_issue;
+      p.prof[blockIdx.x * kPCount + kPEpiPar] = t_par;
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  __syncwarp();                                      // the single-lane roles rejoin their warps first
+  ptx::cluster_sync();                               // nobody exits (or frees TMEM) while its peer is still working
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
   }
   if (prof && threadIdx.x == 0) p.prof[blockIdx.x * kPCount + kPTotal] = clock64() - t_start;
 }
@@ -420,9 +456,10 @@ metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream)
                                     kSmemLimit));
     configured = true;
   }
-  const int tiles = L.prm.m_tiles * L.prm.n_tiles;
-  if (tiles == 0) return METRO_OK;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int pair_tiles = ((L.prm.m_tiles + 1) / 2) * L.prm.n_tiles;
+  if (pair_tiles == 0) return METRO_OK;
+  const int max_pairs = num_sms / 2;
+  const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // CTA pairs (cluster of 2)
   conv_gemm_kernel<BLOCK_N, kMode><<<grid, kThreads, L.prm.smem_bytes, stream>>>(L.prm);
   METRO_CUDA(cudaGetLastError());
   return METRO_OK;
@@ -487,7 +524,7 @@ metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout
   if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[2] = {cuuint64_t(k_total), cuuint64_t(cout_pad)};
   const cuuint64_t strides[1] = {cuuint64_t(k_total) * 2};
-  const cuuint32_t box[2] = {cuuint32_t(kTileK), cuuint32_t(block_n)};
+  const cuuint32_t box[2] = {cuuint32_t(kTileK), cuuint32_t(block_n / 2)};   // one CTA's half of the rows
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -508,7 +545,7 @@ int conv_gemm_pick_block_n(int cout, bool direct) {
 metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks) {
   (void)k_blocks;
   ConvGemmParams &p = L.prm;
-  const int stage_bytes = kTileM * kTileK * 2 + L.block_n * kTileK * 2;
+  const int stage_bytes = kTileM * kTileK * 2 + (L.block_n / 2) * kTileK * 2;
   const int n_out = L.direct ? 0 : (p.has_out1 ? 1 : 0) + (p.has_out2 ? 1 : 0);
   const int par_bytes = 2 * (p.has_out2 ? 3 : 2) * L.block_n * 4;     // two epilogue groups
   const int stage_out = kEpilogueWarps * n_out * kWarpStageBytes;

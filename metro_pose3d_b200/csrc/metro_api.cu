@@ -446,7 +446,7 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
   int li = 1;
   for (auto &L : h->gemms) {
     conv_gemm_set_batch(L.prm, n);
-    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li) * h->num_sms * 8 : nullptr;
+    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li) * h->num_sms * 16 : nullptr;
     ++li;
     if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
@@ -670,7 +670,7 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
   Timer t;
   if (!h) return fail(METRO_ERR_VALUE, "handle is null");
   const bool roles = getenv("METRO_ROLE_PROF") != nullptr;
-  const size_t role_elems = size_t(h->gemms.size() + 1) * h->num_sms * 8;
+  const size_t role_elems = size_t(h->gemms.size() + 1) * h->num_sms * 16;
   if (roles) {
     METRO_CUDA(cudaMalloc(&t.role_prof, role_elems * sizeof(long long)));
     METRO_CUDA(cudaMemset(t.role_prof, 0, role_elems * sizeof(long long)));
@@ -685,22 +685,24 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
     std::vector<long long> host(role_elems);
     METRO_CUDA(cudaMemcpy(host.data(), t.role_prof, role_elems * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(t.role_prof);
-    fprintf(stderr, "%-28s %9s %9s %9s %9s %9s %9s %9s %6s\n", "roles (kcycles, CTA mean)", "total", "prod_wait", "mma_full",
-            "mma_acc", "epi_wait", "epi_busy", "st_wait", "tiles");
+    fprintf(stderr, "%-28s %9s %9s %9s %9s %9s %9s %9s %6s %8s %8s %8s %8s %8s %8s %8s %8s\n", "roles (kcycles, CTA mean)", "total", "prod_wait", "mma_full",
+            "mma_acc", "epi_wait", "epi_busy", "st_wait", "tiles", "e_ld", "e_math", "e_sts", "e_issue", "e_par", "m_issue", "m_commit", "p_issue");
     for (size_t l = 0; l <= h->gemms.size(); ++l) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      double acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       int ctas = 0;
       for (int c = 0; c < h->num_sms; ++c) {
-        const long long *r = &host[(l * h->num_sms + c) * 8];
+        const long long *r = &host[(l * h->num_sms + c) * 16];
         if (r[0] == 0) continue;
         ++ctas;
-        for (int k = 0; k < 8; ++k) acc[k] += double(r[k]);
+        for (int k = 0; k < 16; ++k) acc[k] += double(r[k]);
       }
       if (!ctas) continue;
+      acc[2] *= 2; acc[3] *= 2; acc[7] *= 2; acc[13] *= 2; acc[14] *= 2;        // MMA-thread columns exist in the pair leaders only
       const std::string &nm = l == 0 ? h->root_gemm.name : h->gemms[l - 1].name;
-      fprintf(stderr, "%-28s %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %6.1f\n", nm.c_str(), acc[0] / ctas / 1e3,
+      fprintf(stderr, "%-28s %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %6.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f\n", nm.c_str(), acc[0] / ctas / 1e3,
               acc[1] / ctas / 1e3, acc[2] / ctas / 1e3, acc[3] / ctas / 1e3, acc[4] / ctas / 1e3, acc[5] / ctas / 1e3,
-              acc[6] / ctas / 1e3, acc[7] / ctas);
+              acc[6] / ctas / 1e3, acc[7] / ctas, acc[8] / ctas / 1e3, acc[9] / ctas / 1e3, acc[10] / ctas / 1e3,
+              acc[11] / ctas / 1e3, acc[12] / ctas / 1e3, acc[13] / ctas / 1e3, acc[14] / ctas / 1e3, acc[15] / ctas / 1e3);
     }
   }
   std::string names;
