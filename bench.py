@@ -40,39 +40,69 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled through NVML
+    every 5 ms (nvidia-smi itself takes ~100 ms per query, longer than a short timed region)."""
 
     def __init__(self, gpu_index=0):
         super().__init__(daemon=True)
         self.gpu, self.samples, self._stop_evt = gpu_index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+        except Exception:
+            pw = None
+        return mhz, r, pw
 
     def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                      '-i', str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                f = [s.strip() for s in out.strip().split(',')]
-                if len(f) >= 8:
-                    self.samples.append(f)
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.gpu)],
+                                         capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(',')]
+                    bits = 0
+                    for bit, v in zip((0x8, 0x40, 0x20, 0x4), f[3:7]):
+                        if v.lower().startswith('active'):
+                            bits |= bit
+                    self.max_mhz = float(f[1])
+                    self.samples.append((float(f[0]), bits, float(f[2])))
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
-        mx = [float(s[2]) for s in self.samples if s[2].replace('.', '').isdigit()]
+        names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
         reasons = set()
-        for s in self.samples:
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[4:8]):
-                if v.lower().startswith('active'):
+        for _, r, _ in self.samples:
+            for bit, name in names.items():
+                if r & bit:
                     reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(self.samples)}
+        sm = [s[0] for s in self.samples]
+        pw = [s[2] for s in self.samples if s[2] is not None]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(getattr(self, 'max_mhz', 0)) or None,
+                'reasons': sorted(reasons), 'samples': len(self.samples), 'power_w_max': max(pw) if pw else None}
 
 
 def cpu_oracle_rate(spec, weights, dataset, n_sample, threads, repeats=1):
@@ -290,10 +320,10 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = 4
-        rate, dt = cpu_oracle_rate(spec, weights, dataset, sample, cores, repeats=2)
+        sample, passes = 64, 3                     # ~10-20 s of CPU work on the box's host cores
+        rate, dt = cpu_oracle_rate(spec, weights, dataset, sample, cores, repeats=passes)
         cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': f'{sample} crops x 2 passes of config {args.config} ({dt:.2f} s/pass), torch-CPU fp32 oracle port (not TF 1.13)'}
+               'sample': f'{sample} crops x {passes} passes of config {args.config} ({dt:.2f} s/pass), torch-CPU fp32 oracle port (not TF 1.13)'}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

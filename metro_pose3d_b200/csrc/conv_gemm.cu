@@ -155,6 +155,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         int n0, h0;
         if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
         else { n0 = mt * p.nb; h0 = 0; }
+        n0 += p.n_base;
         const int ncol = nt * BLOCK_N + int(rank) * (BLOCK_N / 2);   // this CTA's half of the weight rows
         int kcol = 0;                               // K coordinate in the packed weight matrix
         for (int tap = 0; tap < p.taps; ++tap) {
@@ -254,7 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint32_t k = 0;
     for (int tile = pair + g * n_pairs; tile < n_tiles_total; tile += 2 * n_pairs, ++k) {
       const int mp = tile / p.n_tiles, nt = tile - mp * p.n_tiles;
-      const int m0 = (2 * mp + int(rank)) * kTileM + q * 32;
+      const int m0 = p.m_base + (2 * mp + int(rank)) * kTileM + q * 32;
       const long long tp0 = prof ? clock64() : 0;
       if (nt != cur_nt) {                            // per-channel epilogue vectors of this N tile
         if (cur_nt >= 0) ptx::named_bar_sync(1 + g, 128);   // the group is done with the previous ones
@@ -576,9 +577,12 @@ metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side) {
   return METRO_OK;
 }
 
-metro_status conv_gemm_set_batch(ConvGemmParams &p, int n) {
-  p.m_total = n * p.ho * p.wo;
-  p.m_tiles = (p.m_total + kTileM - 1) / kTileM;
+metro_status conv_gemm_set_batch(ConvGemmParams &p, int n, int n_base) {
+  const int rows = n * p.ho * p.wo;
+  p.n_base = n_base;
+  p.m_base = n_base * p.ho * p.wo;
+  p.m_total = p.m_base + rows;                     // end of the slice (absolute row)
+  p.m_tiles = (rows + kTileM - 1) / kTileM;
   return METRO_OK;
 }
 

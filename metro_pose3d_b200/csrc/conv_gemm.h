@@ -31,6 +31,7 @@ struct alignas(64) ConvGemmParams {
   signed char tap_map[12], tap_dh[12], tap_dw[12];
   // M tiling: a tile is 128 consecutive output pixels = th full rows of nb images
   int m_total, wo, ho, th, nb, tiles_per_img, m_tiles, n_tiles, cout;
+  int n_base, m_base;    // first crop / first output row of the batch slice this launch works on
   // epilogue: y = acc*scale + shift (+ res) ; relu? ; store y (fp16|fp32) ;
   //           y2 = relu(fp16(y)*scale2 + shift2) -> fp16 (the consumer's pre-activation)
   const float *scale, *shift, *scale2, *shift2;
@@ -63,8 +64,8 @@ int conv_gemm_pick_block_n(int cout, bool direct);
 int conv_gemm_cout_pad(int cout, int block_n);
 // Lays out shared memory (stage count, staging buffers) once block_n and the has_* flags are set.
 metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks);
-// Fills the M-tiling fields for `n` images of an out_side x out_side output.
-metro_status conv_gemm_set_batch(ConvGemmParams &p, int n);
+// Fills the M-tiling fields for `n` images (crops n_base .. n_base + n of the buffers) of an out_side x out_side output.
+metro_status conv_gemm_set_batch(ConvGemmParams &p, int n, int n_base = 0);
 metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side);
 metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream);
 // Packs HWIO float32 filters into [cout_pad][K] fp16 in the kernel's K-block order; `w2` (1x1,

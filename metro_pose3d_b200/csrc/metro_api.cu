@@ -213,8 +213,11 @@ struct metro_handle {
   void *sam_ws = nullptr;
   std::map<std::string, std::pair<const void *, size_t>> debug;   // name -> (buffer, elems per crop)
   // host-buffer path
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   float *stage_img = nullptr, *stage_pose = nullptr;
+  int host_chunk = 64;    // crops per PCIe slice of metro_infer_host (METRO_HOST_CHUNK)
+  int stem_gemms = 0;     // tensor-core convolutions that run per slice (up to the last 32x32-or-larger block)
 };
 
 namespace {
@@ -323,6 +326,13 @@ metro_status build_handle(metro_handle &h, const float *blob) {
   h.debug["pool1"] = {cur_raw, pool_elems};
 
   // ---- residual units ----
+  // The leading units whose maps are 32x32 or larger form the "stem" that metro_infer_host runs slice by
+  // slice (a 64-crop slice still gives >= 256 pair tiles per layer).  The outputs of the last stem unit
+  // are what the whole-batch tail reads after every slice has passed, so they get buffers of their own:
+  // the rotating buffers are re-used, in other layouts, by the next slice's early layers.
+  size_t stem_units = 0;
+  while (stem_units < pl.units.size() && pl.units[stem_units].out_side >= 32) ++stem_units;
+  h.stem_gemms = int(3 * stem_units);
   for (size_t i = 0; i < pl.units.size(); ++i) {
     const UnitPlan &u = pl.units[i];
     const bool last = (i + 1 == pl.units.size());
@@ -334,6 +344,8 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     if (keep) {
       if ((st = alloc_half(&b1, e1)) != METRO_OK) return st;
       if ((st = alloc_half(&b2, e2)) != METRO_OK) return st;
+    }
+    if (keep || i + 1 == stem_units) {
       if ((st = alloc_half(&nraw, eo)) != METRO_OK) return st;
       if ((st = alloc_half(&npre, eo)) != METRO_OK) return st;
     }
@@ -384,6 +396,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     }
     cur_raw = nraw; cur_pre = npre;
   }
+  if (const char *e = getenv("METRO_HOST_CHUNK")) h.host_chunk = atoi(e);
   // ---- logits (resnet_v2.py:234-236) -> head tensor ----
   {
     const size_t eh = size_t(pl.feat_side) * pl.feat_side * pl.logits.cout;
@@ -420,12 +433,10 @@ struct Timer {
   long long *role_prof = nullptr;   // device [launch][num_sms][8] role timers (METRO_ROLE_PROF=1)
 };
 
-metro_status run(metro_handle *h, const void *images, bool u8, int n, float *poses, cudaStream_t s, Timer *t) {
-  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
-  if (n < 0 || n > h->max_batch) return fail(METRO_ERR_VALUE, "batch %d outside [0, max_batch=%d]", n, h->max_batch);
-  if (n == 0) return METRO_OK;
-  if (!images || !poses) return fail(METRO_ERR_VALUE, "null image / pose buffer");
-  METRO_CUDA(cudaSetDevice(h->device));
+// Launches the stem (space-to-depth pack, conv1, pool1 and the first `stem_gemms` tensor-core
+// convolutions) for crops [n_base, n_base + n) of the handle's buffers; `images` points at crop n_base.
+metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n_base, int stem_gemms, cudaStream_t s,
+                      Timer *t) {
   const NetPlan &pl = h->plan;
   metro_status st;
   auto mark = [&](const char *name) {
@@ -433,21 +444,39 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
     t->ev.push_back(e); t->names.push_back(name);
   };
-  mark("start");
-  if ((st = s2d_pack_launch(images, u8, h->buf_s2d, n, pl.proc_side, h->s2d_hp, h->s2d_wp, h->s2d_win, s)) != METRO_OK) return st;
+  const size_t s2d_px = size_t(h->s2d_hp) * h->s2d_wp * h->s2d_win * 16;      // fp16 elements per crop
+  if ((st = s2d_pack_launch(images, u8, h->buf_s2d + n_base * s2d_px, n, pl.proc_side, h->s2d_hp, h->s2d_wp, h->s2d_win, s)) != METRO_OK) return st;
   mark("s2d_pack");
-  conv_gemm_set_batch(h->root_gemm.prm, n);
+  conv_gemm_set_batch(h->root_gemm.prm, n, n_base);
   h->root_gemm.prm.prof = (t && t->role_prof) ? t->role_prof : nullptr;
   if ((st = conv_gemm_launch(h->root_gemm, h->num_sms, s)) != METRO_OK) return st;
   mark("conv1");
-  if ((st = pool_preact_launch(h->buf_root, h->pool_raw, h->pool_pre, h->d_pool_scale, h->d_pool_shift, n, pl.pool_in,
-                               pl.pool_out, 64, s)) != METRO_OK) return st;
+  const size_t root_px = size_t(pl.pool_in) * pl.pool_in * 64, pool_px = size_t(pl.pool_out) * pl.pool_out * 64;
+  if ((st = pool_preact_launch(h->buf_root + n_base * root_px, h->pool_raw + n_base * pool_px, h->pool_pre + n_base * pool_px,
+                               h->d_pool_scale, h->d_pool_shift, n, pl.pool_in, pl.pool_out, 64, s)) != METRO_OK) return st;
   mark("pool1");
-  int li = 1;
-  for (auto &L : h->gemms) {
-    conv_gemm_set_batch(L.prm, n);
-    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li) * h->num_sms * 16 : nullptr;
-    ++li;
+  for (int li = 0; li < stem_gemms; ++li) {
+    ConvGemmLaunch &L = h->gemms[li];
+    conv_gemm_set_batch(L.prm, n, n_base);
+    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
+    if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
+    mark(L.name.c_str());
+  }
+  return METRO_OK;
+}
+
+// The remaining convolutions, the logits head and the soft-argmax for crops [0, n).
+metro_status run_tail(metro_handle *h, int n, int first_gemm, float *poses, cudaStream_t s, Timer *t) {
+  metro_status st;
+  auto mark = [&](const char *name) {
+    if (!t) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+    t->ev.push_back(e); t->names.push_back(name);
+  };
+  for (size_t li = first_gemm; li < h->gemms.size(); ++li) {
+    ConvGemmLaunch &L = h->gemms[li];
+    conv_gemm_set_batch(L.prm, n, 0);
+    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
@@ -459,6 +488,21 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
   if ((st = softargmax_launch(sl, s)) != METRO_OK) return st;
   mark("softargmax");
   return METRO_OK;
+}
+
+metro_status run(metro_handle *h, const void *images, bool u8, int n, float *poses, cudaStream_t s, Timer *t) {
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  if (n < 0 || n > h->max_batch) return fail(METRO_ERR_VALUE, "batch %d outside [0, max_batch=%d]", n, h->max_batch);
+  if (n == 0) return METRO_OK;
+  if (!images || !poses) return fail(METRO_ERR_VALUE, "null image / pose buffer");
+  METRO_CUDA(cudaSetDevice(h->device));
+  if (t) {
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+    t->ev.push_back(e); t->names.push_back("start");
+  }
+  metro_status st = run_stem(h, images, u8, n, 0, 0, s, t);
+  if (st != METRO_OK) return st;
+  return run_tail(h, n, 0, poses, s, t);
 }
 
 }  // namespace
@@ -529,6 +573,8 @@ metro_status metro_destroy(metro_handle *h) {
   if (!h) return METRO_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (auto e : h->ev_copied) if (e) cudaEventDestroy(e);
   if (h->stage_img) cudaFree(h->stage_img);
   if (h->stage_pose) cudaFree(h->stage_pose);
   delete h;
@@ -555,15 +601,36 @@ metro_status metro_infer_host(metro_handle *h, const float *images_host, int32_t
   if (n == 0) return METRO_OK;
   if (!images_host || !poses_host) return fail(METRO_ERR_VALUE, "null image / pose buffer");
   METRO_CUDA(cudaSetDevice(h->device));
-  const size_t img_bytes = size_t(h->plan.proc_side) * h->plan.proc_side * 3 * sizeof(float);
+  const size_t img_elems = size_t(h->plan.proc_side) * h->plan.proc_side * 3;
+  const size_t img_bytes = img_elems * sizeof(float);
   const size_t pose_bytes = h->perm.size() * 3 * sizeof(float);
   if (!h->stream) {
     METRO_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    METRO_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     METRO_CUDA(cudaMalloc(&h->stage_img, img_bytes * h->max_batch));
     METRO_CUDA(cudaMalloc(&h->stage_pose, pose_bytes * h->max_batch));
+    for (int i = 0; i < 2; ++i) {
+      METRO_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    }
   }
-  METRO_CUDA(cudaMemcpyAsync(h->stage_img, images_host, img_bytes * n, cudaMemcpyHostToDevice, h->stream));
-  const metro_status st = run(h, h->stage_img, false, n, h->stage_pose, h->stream, nullptr);
+  // The crops arrive over PCIe in slices; the stem of the network (root, block1, block2: the layers whose
+  // tile count per crop is large, so that a slice still fills the GPU) runs slice by slice underneath the
+  // copies, the deep blocks (few, large tiles per crop) run once on the whole batch.  A crop's result does
+  // not depend on the slicing (every tile holds whole rows of one crop).
+  int chunk = h->host_chunk;
+  if (chunk <= 0 || chunk >= n) chunk = n;
+  const int stem_gemms = chunk < n ? h->stem_gemms : 0;
+  int i = 0;
+  for (int lo = 0; lo < n; lo += chunk, ++i) {
+    const int cnt = lo + chunk <= n ? chunk : n - lo;
+    METRO_CUDA(cudaMemcpyAsync(h->stage_img + size_t(lo) * img_elems, images_host + size_t(lo) * img_elems, img_bytes * cnt,
+                               cudaMemcpyHostToDevice, h->copy_stream));
+    METRO_CUDA(cudaEventRecord(h->ev_copied[i & 1], h->copy_stream));
+    METRO_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied[i & 1], 0));
+    const metro_status st = run_stem(h, h->stage_img + size_t(lo) * img_elems, false, cnt, lo, stem_gemms, h->stream, nullptr);
+    if (st != METRO_OK) return st;
+  }
+  const metro_status st = run_tail(h, n, stem_gemms, h->stage_pose, h->stream, nullptr);
   if (st != METRO_OK) return st;
   METRO_CUDA(cudaMemcpyAsync(poses_host, h->stage_pose, pose_bytes * n, cudaMemcpyDeviceToHost, h->stream));
   METRO_CUDA(cudaStreamSynchronize(h->stream));

@@ -89,6 +89,20 @@ def test_host_buffer_call_and_batch_invariance():
         model.infer_host(np.zeros((9, 256, 256, 3), np.float32))      # > max_batch
 
 
+def test_sliced_host_path_equals_device_path():
+    """metro_infer_host runs the stem of the network slice by slice underneath the PCIe copies (64-crop
+    slices, ragged last one) and the deep blocks on the whole batch: bit-identical to the device-buffer call."""
+    import torch
+    from metro_pose3d_b200.inference import MetroModel
+    n = 160                                       # 64 + 64 + 32
+    model = MetroModel('resnet_v2_50', 16, 'h36m', max_batch=n)
+    img = torch.rand((n, 256, 256, 3), dtype=torch.float32)
+    a = model.infer(img.cuda()).cpu().numpy()
+    b = model.infer_host(img.numpy())
+    assert np.array_equal(a, b)
+    assert np.isfinite(a).all() and np.abs(a).max() > 1.0
+
+
 def test_uint8_ingestion_matches_float_path():
     import torch
     from metro_pose3d_b200.inference import MetroModel
