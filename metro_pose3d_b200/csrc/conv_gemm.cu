@@ -131,7 +131,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0, t_issue = 0;
@@ -187,7 +187,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kTileM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0, it = 0;
