@@ -235,7 +235,9 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope): the TMEM hand-over is ordered by tcgen05.wait::ld +
+  // tcgen05.fence::before_thread_sync; a cluster-scope release would compile to a GPU-wide MEMBAR per tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion bytes are signalled on a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const void *desc, uint32_t bar_cluster_addr, int c0,
