@@ -31,7 +31,7 @@ namespace metro {
 
 namespace {
 
-constexpr int kCtrlWarps = 4;                 // 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle
+constexpr int kCtrlWarps = 4;                 // 0 = TMA producer (A), 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA producer (B)
 constexpr int kEpiWarps = 8;                  // two groups of four; group g drains accumulator stage g
 constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32;
 constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
@@ -42,7 +42,12 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int kABytes = kTileM * kTileK * 2;          // 16 KB: this CTA's 128 pixel rows
   static constexpr int kBBytes = (BLOCK_N / 2) * kTileK * 2;   // this CTA's half of the weight rows
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBlockBytes = kABytes + kBBytes;        // one 64-channel K block
+  // K blocks per pipeline stage (one barrier round trip, one commit): the per-stage cost of the two
+  // single-thread roles (~250 cycles) has to stay below the stage's MMA time, which is only
+  // 4 x 56 / 64 cycles per K block for narrow tiles
+  static constexpr int kSub = BLOCK_N <= 160 ? 2 : 1;
+  static constexpr int kStageBytes = kSub * kBlockBytes;
   static constexpr int kAccCols = BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256);  // per accumulator stage
   static constexpr int kTmemCols = 2 * kAccCols;               // power of two >= 32
 };
@@ -129,26 +134,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0) {
-    // ================================ TMA producer ================================
+  if (warp == 0 || warp == 3) {
+    // ================================ TMA producers ===============================
+    // Two single-thread producers walk the same K-block sequence: warp 0 fetches the activation boxes
+    // (A) and arms the stage's byte count, warp 3 fetches the weight boxes (B).  One thread can retire a
+    // wait -> arm -> issue chain only every ~400 cycles (tools/ubench/tma_rate.cu: 396 cycles per box
+    // whatever its size), so the two operand streams must not share a thread.
     if (ptx::elect_one()) {
+      const bool is_a = warp == 0;
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0, t_issue = 0;
-      // operands of both CTAs land on the LEADER's full barrier (it alone arms the byte count)
+      // operands of both CTAs land on the LEADER's full barrier (its A producer alone arms the byte count)
       const uint32_t full0 = ptx::mapa(ptx::smem_u32(full), 0);
+      int sub = 0, left = 0;                        // K block within the stage; K blocks of the tile still to load
       auto acquire = [&]() -> unsigned char * {
-        if (prof) {
-          const long long t0 = clock64();
-          ptx::mbar_wait(empty + stage, phase ^ 1);
-          t_wait += clock64() - t0;
-        } else {
-          ptx::mbar_wait(empty + stage, phase ^ 1);
+        if (sub == 0) {
+          if (prof) {
+            const long long t0 = clock64();
+            ptx::mbar_wait(empty + stage, phase ^ 1);
+            t_wait += clock64() - t0;
+          } else {
+            ptx::mbar_wait(empty + stage, phase ^ 1);
+          }
+          if (is_a && rank == 0) ptx::mbar_arrive_expect_tx(full + stage, 2 * C::kBlockBytes * min(C::kSub, left));
         }
-        if (rank == 0) ptx::mbar_arrive_expect_tx(full + stage, 2 * C::kStageBytes);
-        return tiles + stage * C::kStageBytes;
+        return tiles + stage * C::kStageBytes + sub * C::kBlockBytes;
       };
-      auto advance = [&]() { if (++stage == stages) { stage = 0; phase ^= 1; } };
+      auto advance = [&]() {
+        --left;
+        if (++sub == C::kSub || left == 0) { sub = 0; if (++stage == stages) { stage = 0; phase ^= 1; } }
+      };
       for (int tile = pair; tile < n_tiles_total; tile += n_pairs) {
         const int mp = tile / p.n_tiles, nt = tile - mp * p.n_tiles;
         const int mt = 2 * mp + int(rank);          // this CTA's 128-pixel tile (may be one past the end: zero fill)
@@ -157,33 +173,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         else { n0 = mt * p.nb; h0 = 0; }
         n0 += p.n_base;
         const int ncol = nt * BLOCK_N + int(rank) * (BLOCK_N / 2);   // this CTA's half of the weight rows
-        int kcol = 0;                               // K coordinate in the packed weight matrix
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const CUtensorMap *am = &p.amap[p.tap_map[tap]];
-          const int dw = p.tap_dw[tap], hh = h0 + p.tap_dh[tap];
-          for (int cb = 0; cb < p.cblk0; ++cb, kcol += kTileK) {
-            unsigned char *sa = acquire();
-            const long long i0 = prof ? clock64() : 0;
-            const uint32_t fb = full0 + uint32_t(stage) * 8u;
-            ptx::tma_load_4d_pair(sa, am, fb, cb * kTileK, dw, hh, n0);
-            ptx::tma_load_2d_pair(sa + C::kABytes, &p.bmap, fb, kcol, ncol);
-            advance();
-            if (prof) t_issue += clock64() - i0;
+        const int cb2_0 = p.diag2 ? nt * (BLOCK_N / 64) : 0;
+        const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
+        left = k0 + n2;
+        if (is_a) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const CUtensorMap *am = &p.amap[p.tap_map[tap]];
+            const int dw = p.tap_dw[tap], hh = h0 + p.tap_dh[tap];
+            for (int cb = 0; cb < p.cblk0; ++cb) {
+              unsigned char *sa = acquire();
+              const long long i0 = prof ? clock64() : 0;
+              ptx::tma_load_4d_pair(sa, am, full0 + uint32_t(stage) * 8u, cb * kTileK, dw, hh, n0);
+              advance();
+              if (prof) t_issue += clock64() - i0;
+            }
           }
-        }
-        if (p.cblk1) {
-          const int cb2_0 = p.diag2 ? nt * (BLOCK_N / 64) : 0;
-          const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
           for (int cb = cb2_0; cb < cb2_0 + n2; ++cb) {
             unsigned char *sa = acquire();
-            const uint32_t fb = full0 + uint32_t(stage) * 8u;
-            ptx::tma_load_4d_pair(sa, &p.a2map, fb, cb * kTileK, 0, h0, n0);
-            ptx::tma_load_2d_pair(sa + C::kABytes, &p.bmap, fb, (k0 + cb) * kTileK, ncol);
+            ptx::tma_load_4d_pair(sa, &p.a2map, full0 + uint32_t(stage) * 8u, cb * kTileK, 0, h0, n0);
+            advance();
+          }
+        } else {
+          // weights: K blocks 0 .. k0-1 of source 0, then blocks k0 + cb2_0 .. of the appended source-1 range
+          for (int kb = 0; kb < k0 + n2; ++kb) {
+            const int kcol = (kb < k0 ? kb : kb + cb2_0) * kTileK;
+            unsigned char *sa = acquire();
+            ptx::tma_load_2d_pair(sa + C::kABytes, &p.bmap, full0 + uint32_t(stage) * 8u, kcol, ncol);
             advance();
           }
         }
       }
-      if (prof) { p.prof[blockIdx.x * kPCount + kPProdWait] = t_wait; p.prof[blockIdx.x * kPCount + kPProdIssue] = t_issue; }
+      if (prof && is_a) { p.prof[blockIdx.x * kPCount + kPProdWait] = t_wait; p.prof[blockIdx.x * kPCount + kPProdIssue] = t_issue; }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
@@ -203,7 +223,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = 0; kb < n_kb; kb += C::kSub) {
           {
             const long long t0 = prof ? clock64() : 0;
             ptx::mbar_wait(full + stage, phase);
@@ -215,9 +235,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
           const uint64_t db = ptx::make_sw128_kmajor_desc(sa + C::kABytes);
 #pragma unroll
-          for (int k = 0; k < kTileK / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int sb = 0; sb < C::kSub; ++sb) {
+            if (sb > 0 && kb + sb >= n_kb) break;    // odd K-block count: the last stage is half full
+#pragma unroll
+            for (int k = 0; k < kTileK / 16; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              const uint32_t off = uint32_t(sb * (C::kBlockBytes >> 4) + 2 * k);
+              ptx::umma_f16_pair(d_tmem, da + off, db + off, idesc, (kb | sb | k) != 0);
+            }
           }
           const long long m1 = prof ? clock64() : 0;
           ptx::umma_commit_pair(empty + stage, 3);   // frees the smem slot in both CTAs when these MMAs retire
@@ -546,7 +571,8 @@ int conv_gemm_pick_block_n(int cout, bool direct) {
 metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks) {
   (void)k_blocks;
   ConvGemmParams &p = L.prm;
-  const int stage_bytes = kTileM * kTileK * 2 + (L.block_n / 2) * kTileK * 2;
+  const int k_sub = L.block_n <= 160 ? 2 : 1;      // Cfg::kSub
+  const int stage_bytes = k_sub * (kTileM * kTileK * 2 + (L.block_n / 2) * kTileK * 2);
   const int n_out = L.direct ? 0 : (p.has_out1 ? 1 : 0) + (p.has_out2 ? 1 : 0);
   const int par_bytes = 2 * (p.has_out2 ? 3 : 2) * L.block_n * 4;     // two epilogue groups
   const int stage_out = kEpilogueWarps * n_out * kWarpStageBytes;
