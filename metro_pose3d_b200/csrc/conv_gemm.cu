@@ -133,6 +133,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   ptx::cluster_sync();                               // both CTAs' barriers exist before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) ran while the
+  // previous kernel in the stream was still draining; its outputs may only be touched from here on.
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
 
   if (warp == 0 || warp == 3) {
     // ================================ TMA producers ===============================
@@ -486,8 +490,14 @@ metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream)
   if (pair_tiles == 0) return METRO_OK;
   const int max_pairs = num_sms / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // CTA pairs (cluster of 2)
-  conv_gemm_kernel<BLOCK_N, kMode><<<grid, kThreads, L.prm.smem_bytes, stream>>>(L.prm);
-  METRO_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = size_t(L.prm.smem_bytes); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  METRO_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kMode>, L.prm));
   return METRO_OK;
 }
 

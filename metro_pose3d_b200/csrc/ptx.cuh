@@ -286,6 +286,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t cta_mas
                : "memory");
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// wait: blocks until the grid this one depends on has completed and its memory is visible;
+// launch_dependents: lets the next grid in the stream start launching (its CTAs then sit in their own wait)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- misc ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
