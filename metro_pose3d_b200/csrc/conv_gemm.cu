@@ -34,6 +34,8 @@ namespace {
 constexpr int kCtrlWarps = 4;                 // 0 = TMA producer (A), 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA producer (B)
 constexpr int kEpiWarps = 8;                  // two groups of four; group g drains accumulator stage g
 constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32;
+constexpr int kXformWarps = 4;                // optional: apply the pre-activation to the A tiles in shared memory
+constexpr int kThreadsXform = kThreads + kXformWarps * 32;
 constexpr int kSmemLimit = 232448;            // 227 KB opt-in maximum per CTA on sm_100
 
 enum Mode { kSingle = 0, kDual = 1, kDirect = 2 };
@@ -52,9 +54,9 @@ struct Cfg {
   static constexpr int kTmemCols = 2 * kAccCols;               // power of two >= 32
 };
 
-// barrier block layout (uint64 slots): full[8] empty[8] tfull[2] tempty[2], then the TMEM base
-constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarTFull = 2 * kMaxStages, kBarTEmpty = kBarTFull + 2,
-              kBarCount = kBarTEmpty + 2;
+// barrier block layout (uint64 slots): full[8] empty[8] ready[8] tfull[2] tempty[2], then the TMEM base
+constexpr int kBarFull = 0, kBarEmpty = kMaxStages, kBarReady = 2 * kMaxStages, kBarTFull = 3 * kMaxStages,
+              kBarTEmpty = kBarTFull + 2, kBarCount = kBarTEmpty + 2;
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t d;
@@ -79,8 +81,12 @@ enum Prof { kPTotal = 0, kPProdWait, kPMmaWaitFull, kPMmaWaitAcc, kPEpiWaitAcc, 
 // weight rows per K block (so a stage is 16 KB + BLOCK_N/2 x 128 B and shared-memory write + read
 // traffic per MMA halves against a one-CTA tile), the leader's elected thread issues one M=256 MMA
 // for both tensor cores, and each CTA drains its own 128 accumulator rows from its own TMEM.
-template <int BLOCK_N, int kMode>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+//
+// kXform: the A operand is a unit's RAW input and the unit's pre-activation relu(bn(x)) (resnet_v2.py:119)
+// is applied to each A tile in shared memory by four extra warps between the TMA landing and the MMA, so
+// the producing conv3 does not have to write the pre-activated tensor to HBM at all (1x1 convs only).
+template <int BLOCK_N, int kMode, bool kXform>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXform : kThreads, 1)
     conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BLOCK_N>;
   constexpr int kParVecs = kMode == kDual ? 3 : 2;   // single/direct: scale, shift; dual: shift, scale2, shift2
@@ -93,7 +99,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   }
   unsigned char *tiles = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.off_bar);
-  uint64_t *full = bars + kBarFull, *empty = bars + kBarEmpty;
+  uint64_t *full = bars + kBarFull, *empty = bars + kBarEmpty, *ready = bars + kBarReady;
   uint64_t *tfull = bars + kBarTFull, *tempty = bars + kBarTEmpty;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + kBarCount);
 
@@ -119,7 +125,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < stages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    for (int i = 0; i < stages; ++i) {
+      ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1);
+      ptx::mbar_init(ready + i, 2 * kXformWarps);    // leader's: the transform warps of both CTAs
+    }
     // tempty (the leader's is the one used): the four warps of the group in BOTH CTAs
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, kEpiWarps); }
     ptx::fence_mbar_init();
@@ -150,7 +159,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       long long t_wait = 0, t_issue = 0;
       // operands of both CTAs land on the LEADER's full barrier (its A producer alone arms the byte count)
-      const uint32_t full0 = ptx::mapa(ptx::smem_u32(full), 0);
+      // (with kXform every CTA has its own full barrier: its transform warps wait on it locally)
+      const uint32_t full0 = ptx::mapa(ptx::smem_u32(full), kXform ? rank : 0);
       int sub = 0, left = 0;                        // K block within the stage; K blocks of the tile still to load
       auto acquire = [&]() -> unsigned char * {
         if (sub == 0) {
@@ -161,7 +171,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           } else {
             ptx::mbar_wait(empty + stage, phase ^ 1);
           }
-          if (is_a && rank == 0) ptx::mbar_arrive_expect_tx(full + stage, 2 * C::kBlockBytes * min(C::kSub, left));
+          if (is_a && (kXform || rank == 0))
+            ptx::mbar_arrive_expect_tx(full + stage, (kXform ? 1 : 2) * C::kBlockBytes * min(C::kSub, left));
         }
         return tiles + stage * C::kStageBytes + sub * C::kBlockBytes;
       };
@@ -230,7 +241,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int kb = 0; kb < n_kb; kb += C::kSub) {
           {
             const long long t0 = prof ? clock64() : 0;
-            ptx::mbar_wait(full + stage, phase);
+            ptx::mbar_wait((kXform ? ready : full) + stage, phase);
             if (prof) t_full += clock64() - t0;
           }
           ptx::tc_fence_after();
@@ -261,6 +272,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         p.prof[blockIdx.x * kPCount + kPTiles] = it;
         p.prof[blockIdx.x * kPCount + kPMmaIssue] = t_mi;
         p.prof[blockIdx.x * kPCount + kPMmaCommit] = t_mc;
+      }
+    }
+  } else if (kXform && warp >= kCtrlWarps + kEpiWarps) {
+    // ======================= A-operand transform: x -> relu(x * scale + shift) =======================
+    // thread = one 16-byte chunk (8 channels) of 8 rows of the 128 x 64 tile: the channel vectors stay in
+    // registers for the whole K block, a warp touches 4 whole 128-byte rows per access (conflict-free in
+    // the 128B-swizzled layout), values are rounded to fp16 exactly like the stored pre-activation was.
+    const int xt = threadIdx.x - (kCtrlWarps + kEpiWarps) * 32;     // 0..127
+    const int chunk = xt & 7, row0 = xt >> 3;
+    const float *apar = reinterpret_cast<const float *>(smem + p.off_apar);   // [2][cin]
+    for (int i = xt; i < 2 * p.cblk0 * kTileK; i += kXformWarps * 32) {
+      const int c = i % (p.cblk0 * kTileK);
+      const_cast<float *>(apar)[i] = i < p.cblk0 * kTileK ? p.ascale[c] : p.ashift[c];
+    }
+    ptx::named_bar_sync(3, kXformWarps * 32);
+    const uint32_t ready0 = ptx::mapa(ptx::smem_u32(ready), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < n_tiles_total; tile += n_pairs) {
+      for (int kb = 0; kb < k0; kb += C::kSub) {
+        ptx::mbar_wait(full + stage, phase);
+#pragma unroll
+        for (int sb = 0; sb < C::kSub; ++sb) {
+          if (sb > 0 && kb + sb >= k0) break;
+          const int cb = (kb + sb) % p.cblk0;
+          const float *ps = apar + cb * kTileK + chunk * 8, *pf = ps + p.cblk0 * kTileK;
+          const float4 s0 = *reinterpret_cast<const float4 *>(ps), s1 = *reinterpret_cast<const float4 *>(ps + 4);
+          const float4 f0 = *reinterpret_cast<const float4 *>(pf), f1 = *reinterpret_cast<const float4 *>(pf + 4);
+          const uint32_t base = ptx::smem_u32(tiles + stage * C::kStageBytes + sb * C::kBlockBytes);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row0 + 16 * i;
+            const uint32_t a = base + uint32_t(row) * 128u + (uint32_t(chunk ^ (row & 7)) << 4);
+            uint4 v = ptx::lds_v4u(a);
+            uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2 *>(&w[0]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2 *>(&w[1]));
+            const float2 x2 = __half22float2(*reinterpret_cast<const __half2 *>(&w[2]));
+            const float2 x3 = __half22float2(*reinterpret_cast<const __half2 *>(&w[3]));
+            const float2 y0 = __ffma2_rn(x0, make_float2(s0.x, s0.y), make_float2(f0.x, f0.y));
+            const float2 y1 = __ffma2_rn(x1, make_float2(s0.z, s0.w), make_float2(f0.z, f0.w));
+            const float2 y2 = __ffma2_rn(x2, make_float2(s1.x, s1.y), make_float2(f1.x, f1.y));
+            const float2 y3 = __ffma2_rn(x3, make_float2(s1.z, s1.w), make_float2(f1.z, f1.w));
+            w[0] = pack_relu_f16x2(y0.x, y0.y); w[1] = pack_relu_f16x2(y1.x, y1.y);
+            w[2] = pack_relu_f16x2(y2.x, y2.y); w[3] = pack_relu_f16x2(y3.x, y3.y);
+            sts_v4(a, v);
+          }
+        }
+        ptx::fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ready0 + uint32_t(stage) * 8u);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= kCtrlWarps) {
@@ -478,11 +541,11 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-template <int BLOCK_N, int kMode>
+template <int BLOCK_N, int kMode, bool kXform = false>
 metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kMode, kXform>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemLimit));
     configured = true;
   }
@@ -491,13 +554,13 @@ metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream)
   const int max_pairs = num_sms / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // CTA pairs (cluster of 2)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kThreads);
+  cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kXform ? kThreadsXform : kThreads);
   cfg.dynamicSmemBytes = size_t(L.prm.smem_bytes); cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  METRO_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kMode>, L.prm));
+  METRO_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kMode, kXform>, L.prm));
   return METRO_OK;
 }
 
@@ -586,13 +649,15 @@ metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks) {
   const int n_out = L.direct ? 0 : (p.has_out1 ? 1 : 0) + (p.has_out2 ? 1 : 0);
   const int par_bytes = 2 * (p.has_out2 ? 3 : 2) * L.block_n * 4;     // two epilogue groups
   const int stage_out = kEpilogueWarps * n_out * kWarpStageBytes;
-  int stages = (kSmemLimit - 256 - par_bytes - stage_out) / stage_bytes;
+  const int apar_bytes = p.ascale ? 2 * p.cblk0 * kTileK * 4 : 0;      // pre-activation vectors of the A transform
+  int stages = (kSmemLimit - 256 - par_bytes - apar_bytes - stage_out) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(METRO_ERR_INTERNAL, "conv_gemm: shared memory plan leaves %d stages", stages);
   p.stages = stages;
   int off = stages * stage_bytes;
   p.off_stage = off; off += stage_out;
   p.off_par = off; off += par_bytes;
+  p.off_apar = off; off += apar_bytes;
   p.off_bar = off; off += 256;
   p.smem_bytes = off;
   return METRO_OK;
@@ -673,6 +738,11 @@ metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t
       case 64: return launch_t<64, kDual>(L, num_sms, stream);
       case 128: return launch_t<128, kDual>(L, num_sms, stream);
       case 256: return launch_t<256, kDual>(L, num_sms, stream);
+    }
+  } else if (L.prm.ascale) {
+    switch (L.block_n) {
+      case 64: return launch_t<64, kSingle, true>(L, num_sms, stream);
+      case 128: return launch_t<128, kSingle, true>(L, num_sms, stream);
     }
   } else {
     switch (L.block_n) {

@@ -35,12 +35,14 @@ struct alignas(64) ConvGemmParams {
   // epilogue: y = acc*scale + shift (+ res) ; relu? ; store y (fp16|fp32) ;
   //           y2 = relu(fp16(y)*scale2 + shift2) -> fp16 (the consumer's pre-activation)
   const float *scale, *shift, *scale2, *shift2;
+  // optional A-operand transform (1x1 convs): x -> relu(x * ascale[c] + ashift[c]) applied in shared memory
+  const float *ascale, *ashift;
   void *out1;            // direct-store path only (logits head)
   int out1_f32;
   int has_out1, has_out2, relu1;
   // shared-memory plan (bytes from the 1024-aligned base)
   int stages;
-  int off_stage, off_par, off_bar, smem_bytes;
+  int off_stage, off_par, off_apar, off_bar, smem_bytes;
   long long *prof;       // optional [grid][8] per-CTA role timers (cycles); nullptr = off
 };
 

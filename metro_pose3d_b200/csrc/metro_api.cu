@@ -90,6 +90,7 @@ struct GemmSpec {
   unsigned c_box[4] = {0, 0, 0, 0};
   const __half *src2 = nullptr; int cin2 = 0; const float *w2 = nullptr;
   std::vector<float> scale, shift, scale2, shift2;
+  std::vector<float> ascale, ashift;        // optional pre-activation applied to source 0 inside the kernel (1x1 only)
   bool relu = false;
   const __half *res = nullptr; int res_stride = 0, res_shift = 0, res_side = 0;
   void *out1 = nullptr; bool out1_f32 = false;
@@ -173,6 +174,12 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   if (g.out2) {
     st = arena.upload(&d, g.scale2, cout_pad); if (st != METRO_OK) return st; p.scale2 = d;
     st = arena.upload(&d, g.shift2, cout_pad); if (st != METRO_OK) return st; p.shift2 = d;
+  }
+  if (!g.ascale.empty()) {
+    if (g.k != 1 || g.stride != 1 || g.cin2 || g.res || g.out2 || L.direct || L.block_n > 128 || g.custom_a)
+      return fail(METRO_ERR_VALUE, "%s: the in-kernel pre-activation needs a plain 1x1 convolution with <= 128 outputs", g.name.c_str());
+    st = arena.upload(&d, g.ascale); if (st != METRO_OK) return st; p.ascale = d;
+    st = arena.upload(&d, g.ashift); if (st != METRO_OK) return st; p.ashift = d;
   }
   p.relu1 = g.relu ? 1 : 0;
   p.has_out1 = g.out1 ? 1 : 0; p.has_out2 = g.out2 ? 1 : 0;
@@ -350,9 +357,19 @@ metro_status build_handle(metro_handle &h, const float *blob) {
       if ((st = alloc_half(&npre, eo)) != METRO_OK) return st;
     }
     ConvGemmLaunch L;
+    // An identity unit of block1/block2 (HBM-bound layers, <= 128 bottleneck channels) reads its RAW input and
+    // applies its own pre-activation inside conv1 (conv_gemm kXform), so the previous unit's conv3 writes one
+    // tensor instead of two.  Same arithmetic and rounding as the stored pre-activation, hence bit-identical.
+    auto reads_raw = [&](size_t k) {
+      return !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= 128;
+    };
     // conv1: 1x1, BN, ReLU on the pre-activation (resnet_v2.py:127-128)
     {
       GemmSpec g; g.name = u.conv1.name; g.n_max = N; g.src = cur_pre; g.in_side = u.in_side; g.cin = u.cin;
+      if (reads_raw(i)) {
+        g.src = cur_raw;
+        bn_affine(blob + u.preact_off, u.cin, g.ascale, g.ashift);
+      }
       g.out_side = u.in_side; g.cout = u.cb; g.w = blob + u.conv1.w_off;
       bn_affine(blob + u.conv1.bn_off, u.cb, g.scale, g.shift);
       g.relu = true; g.out1 = b1;
@@ -386,13 +403,13 @@ metro_status build_handle(metro_handle &h, const float *blob) {
       }
       const bool need_raw = keep || (!last && !pl.units[i + 1].proj);
       g.out1 = need_raw ? nraw : nullptr;
-      g.out2 = npre;
+      g.out2 = reads_raw(i + 1) ? nullptr : npre;
       const int64_t next_bn = last ? pl.postnorm_off : pl.units[i + 1].preact_off;
-      bn_affine(blob + next_bn, u.depth, g.scale2, g.shift2);
+      if (g.out2) bn_affine(blob + next_bn, u.depth, g.scale2, g.shift2);
       if ((st = build_gemm(A, g, L)) != METRO_OK) return st;
       h.gemms.push_back(L);
       h.debug[u.name + "/out"] = {need_raw ? nraw : nullptr, eo};
-      h.debug[u.name + "/pre"] = {npre, eo};
+      h.debug[u.name + "/pre"] = {g.out2 ? npre : nullptr, eo};
     }
     cur_raw = nraw; cur_pre = npre;
   }

@@ -103,6 +103,19 @@ def test_sliced_host_path_equals_device_path():
     assert np.isfinite(a).all() and np.abs(a).max() > 1.0
 
 
+def test_in_kernel_preactivation_is_bit_identical():
+    """Production handles let identity units of block1/2 read their raw input and apply the pre-activation
+    inside conv1 (no stored pre-activation tensor); keep_activations handles store every tensor.  Same
+    arithmetic and rounding points, so the poses must agree bit for bit."""
+    import torch
+    from metro_pose3d_b200.inference import MetroModel
+    w = synth_weights(NetSpec('resnet_v2_50', 16, 17), 3)
+    img = torch.from_numpy(synth_images(6, seed=77)).cuda()
+    a = MetroModel('resnet_v2_50', 16, 'h36m', weights=w, max_batch=6).infer(img).cpu().numpy()
+    b = MetroModel('resnet_v2_50', 16, 'h36m', weights=w, max_batch=6, keep_activations=True).infer(img).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
 def test_uint8_ingestion_matches_float_path():
     import torch
     from metro_pose3d_b200.inference import MetroModel
