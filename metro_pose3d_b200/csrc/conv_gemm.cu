@@ -302,8 +302,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
           const float4 f0 = *reinterpret_cast<const float4 *>(pf), f1 = *reinterpret_cast<const float4 *>(pf + 4);
           const uint32_t base = ptx::smem_u32(tiles + stage * C::kStageBytes + sb * C::kBlockBytes);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = row0 + 16 * i;
+          for (int i = 0; i < 128 / (kXformWarps * 4); ++i) {
+            const int row = row0 + kXformWarps * 4 * i;
             const uint32_t a = base + uint32_t(row) * 128u + (uint32_t(chunk ^ (row & 7)) << 4);
             uint4 v = ptx::lds_v4u(a);
             uint32_t *w = reinterpret_cast<uint32_t *>(&v);
@@ -743,6 +743,7 @@ metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t
     switch (L.block_n) {
       case 64: return launch_t<64, kSingle, true>(L, num_sms, stream);
       case 128: return launch_t<128, kSingle, true>(L, num_sms, stream);
+      case 256: return launch_t<256, kSingle, true>(L, num_sms, stream);
     }
   } else {
     switch (L.block_n) {

@@ -176,7 +176,7 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
     st = arena.upload(&d, g.shift2, cout_pad); if (st != METRO_OK) return st; p.shift2 = d;
   }
   if (!g.ascale.empty()) {
-    if (g.k != 1 || g.stride != 1 || g.cin2 || g.res || g.out2 || L.direct || L.block_n > 128 || g.custom_a)
+    if (g.k != 1 || g.stride != 1 || g.cin2 || g.res || g.out2 || L.direct || L.block_n > 256 || g.custom_a)
       return fail(METRO_ERR_VALUE, "%s: the in-kernel pre-activation needs a plain 1x1 convolution with <= 128 outputs", g.name.c_str());
     st = arena.upload(&d, g.ascale); if (st != METRO_OK) return st; p.ascale = d;
     st = arena.upload(&d, g.ashift); if (st != METRO_OK) return st; p.ashift = d;
@@ -357,11 +357,12 @@ metro_status build_handle(metro_handle &h, const float *blob) {
       if ((st = alloc_half(&npre, eo)) != METRO_OK) return st;
     }
     ConvGemmLaunch L;
-    // An identity unit of block1/block2 (HBM-bound layers, <= 128 bottleneck channels) reads its RAW input and
+    // An identity unit of block1-3 (<= 256 bottleneck channels; measured: block4's K = 2048 conv1 loses more to the
+    // extra shared-memory pass than its conv3 gains) reads its RAW input and
     // applies its own pre-activation inside conv1 (conv_gemm kXform), so the previous unit's conv3 writes one
     // tensor instead of two.  Same arithmetic and rounding as the stored pre-activation, hence bit-identical.
     auto reads_raw = [&](size_t k) {
-      return !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= 128;
+      return !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= 256;
     };
     // conv1: 1x1, BN, ReLU on the pre-activation (resnet_v2.py:127-128)
     {
