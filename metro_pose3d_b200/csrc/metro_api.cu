@@ -209,11 +209,10 @@ struct metro_handle {
   std::vector<int32_t> perm;
   NetPlan plan;
   DeviceArena arena;
-  // root: space-to-depth pack -> tensor-core conv1 -> pool1 + first pre-activation
-  float *d_pool_scale = nullptr, *d_pool_shift = nullptr;
-  __half *buf_s2d = nullptr, *buf_root = nullptr, *pool_raw = nullptr, *pool_pre = nullptr;
-  int s2d_win = 1, s2d_hp = 0, s2d_wp = 0;
-  ConvGemmLaunch root_gemm;
+  // root: image pack -> fused conv1 + pool1 + first pre-activation
+  float *d_pool_scale = nullptr, *d_pool_shift = nullptr, *d_root_bias = nullptr;
+  __half *buf_packed = nullptr, *buf_root = nullptr, *d_root_w = nullptr, *pool_raw = nullptr, *pool_pre = nullptr;
+  alignas(64) unsigned char image_map[128];
   std::vector<ConvGemmLaunch> gemms;
   void *buf_head = nullptr;
   SoftargmaxLaunch sam{};
@@ -253,54 +252,23 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     return s;
   };
 
-  // ---- root: conv1 7x7/2 (pad 3,3) as a 4x4 stride-1 conv on the 2x2 space-to-depth image ----
-  // s2d pixel (h2,w2) holds input pixels (2h2+p, 2w2+q), channel (p*2+q)*3+ch, padded 12 -> 16; the
-  // buffer carries 2 zero rows/cols before and 1 after (131 = 128 + 3).  Input row 2*ho + kh - 3 is
-  // s2d row ho + dh, parity p with kh = 2*dh + p + 3, dh in [-2,1]: four row taps, and the four column
-  // taps x 16 channels are 64 contiguous fp16 = one 128-byte K block, fetched through a tensor map
-  // whose pixel stride (32 B) is smaller than its row extent (overlapping windows; win = 1).  If the
-  // driver rejects that map the windows are materialised instead (win = 4).
+  // ---- root: image pack -> fused conv1 7x7/2 + bias -> zero-padded pool1 -> first pre-activation (root_fused.cu) ----
   {
-    const int side = pl.pool_in;                      // 128
-    h.s2d_hp = side + 3;
-    std::vector<__half> wp(size_t(64) * 256, __float2half_rn(0.f));
-    const float *w = blob + pl.root.w_off;            // HWIO [7][7][3][64]
-    for (int dhi = 0; dhi < 4; ++dhi)
-      for (int dwi = 0; dwi < 4; ++dwi)
-        for (int pp = 0; pp < 2; ++pp)
-          for (int qq = 0; qq < 2; ++qq) {
-            const int kh = 2 * dhi + pp - 1, kw = 2 * dwi + qq - 1;
-            if (kh < 0 || kw < 0) continue;
-            for (int ch = 0; ch < 3; ++ch)
-              for (int o = 0; o < 64; ++o)
-                wp[size_t(o) * 256 + (dhi * 4 + dwi) * 16 + pp * 6 + qq * 3 + ch] =
-                    __float2half_rn(w[((size_t(kh) * 7 + kw) * 3 + ch) * 64 + o]);
-          }
-    if ((st = alloc_half(&h.buf_root, size_t(side) * side * 64)) != METRO_OK) return st;
-    h.debug["conv1"] = {h.buf_root, size_t(side) * side * 64};
-    GemmSpec g; g.name = "conv1"; g.n_max = N; g.out_side = side; g.cout = 64;
-    g.custom_a = true; g.c_taps = 4; g.w_packed_host = wp.data(); g.k_packed = 256;
-    g.scale.assign(64, 1.0f);
-    g.shift.assign(blob + pl.root.b_off, blob + pl.root.b_off + 64);
-    g.out1 = h.buf_root;
-    const char *force = getenv("METRO_S2D_WIN");
-    for (int win : {1, 4}) {
-      if (force && atoi(force) != win) continue;
-      h.s2d_win = win;
-      h.s2d_wp = (win == 1) ? side + 3 : side;
-      const size_t px_bytes = size_t(win) * 32;
-      void *q = nullptr;
-      if ((st = A.alloc(&q, size_t(N) * h.s2d_hp * h.s2d_wp * px_bytes)) != METRO_OK) return st;
-      h.buf_s2d = static_cast<__half *>(q);
-      g.src = h.buf_s2d;
-      g.c_dims[0] = 64; g.c_dims[1] = side; g.c_dims[2] = h.s2d_hp; g.c_dims[3] = N;
-      g.c_strides[0] = px_bytes; g.c_strides[1] = size_t(h.s2d_wp) * px_bytes;
-      g.c_strides[2] = size_t(h.s2d_hp) * h.s2d_wp * px_bytes;
-      g.c_box[0] = 64; g.c_box[1] = side; g.c_box[2] = 1; g.c_box[3] = 1;
-      st = build_gemm(A, g, h.root_gemm);
-      if (st == METRO_OK) break;
+    if (pl.proc_side != 256 || pl.pool_in != 128 || pl.pool_out != 64)
+      return fail(METRO_ERR_VALUE, "the root kernel is built for 256x256 crops (FLAGS.proc_side)");
+    void *q = nullptr;
+    if ((st = A.alloc(&q, size_t(N) * root_packed_image_elems() * sizeof(__half))) != METRO_OK) return st;
+    h.buf_packed = static_cast<__half *>(q);
+    if ((st = root_make_image_map(h.image_map, h.buf_packed, N)) != METRO_OK) return st;
+    std::vector<__half> wp(root_packed_weight_elems());
+    root_pack_weights(blob + pl.root.w_off, wp.data());
+    if ((st = A.upload(&h.d_root_w, wp)) != METRO_OK) return st;
+    std::vector<float> bias(blob + pl.root.b_off, blob + pl.root.b_off + 64);
+    if ((st = A.upload(&h.d_root_bias, bias)) != METRO_OK) return st;
+    if (keep) {
+      if ((st = alloc_half(&h.buf_root, size_t(pl.pool_in) * pl.pool_in * 64)) != METRO_OK) return st;
+      h.debug["conv1"] = {h.buf_root, size_t(pl.pool_in) * pl.pool_in * 64};
     }
-    if (st != METRO_OK) return st;
   }
   // ---- sizes of the rotating buffers ----
   size_t raw_elems = size_t(pl.pool_out) * pl.pool_out * 64, r1_elems = 0, r2_elems = 0;
@@ -462,17 +430,12 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
     t->ev.push_back(e); t->names.push_back(name);
   };
-  const size_t s2d_px = size_t(h->s2d_hp) * h->s2d_wp * h->s2d_win * 16;      // fp16 elements per crop
-  if ((st = s2d_pack_launch(images, u8, h->buf_s2d + n_base * s2d_px, n, pl.proc_side, h->s2d_hp, h->s2d_wp, h->s2d_win, s)) != METRO_OK) return st;
-  mark("s2d_pack");
-  conv_gemm_set_batch(h->root_gemm.prm, n, n_base);
-  h->root_gemm.prm.prof = (t && t->role_prof) ? t->role_prof : nullptr;
-  if ((st = conv_gemm_launch(h->root_gemm, h->num_sms, s)) != METRO_OK) return st;
-  mark("conv1");
-  const size_t root_px = size_t(pl.pool_in) * pl.pool_in * 64, pool_px = size_t(pl.pool_out) * pl.pool_out * 64;
-  if ((st = pool_preact_launch(h->buf_root + n_base * root_px, h->pool_raw + n_base * pool_px, h->pool_pre + n_base * pool_px,
-                               h->d_pool_scale, h->d_pool_shift, n, pl.pool_in, pl.pool_out, 64, s)) != METRO_OK) return st;
-  mark("pool1");
+  (void)pl;
+  if ((st = img_pack_launch(images, u8, h->buf_packed + size_t(n_base) * root_packed_image_elems(), n, s)) != METRO_OK) return st;
+  mark("img_pack");
+  if ((st = root_fused_launch(h->image_map, h->d_root_w, h->d_root_bias, h->d_pool_scale, h->d_pool_shift,
+                              h->spec.keep_activations ? h->pool_raw : nullptr, h->pool_pre, h->buf_root, n, n_base, h->num_sms, s)) != METRO_OK) return st;
+  mark("conv1+pool1");
   for (int li = 0; li < stem_gemms; ++li) {
     ConvGemmLaunch &L = h->gemms[li];
     conv_gemm_set_batch(L.prm, n, n_base);
@@ -746,7 +709,7 @@ metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf,
 
 metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launches) {
   if (!h || !launches) return fail(METRO_ERR_VALUE, "null argument");
-  *launches = n > 0 ? int32_t(h->gemms.size()) + 4 : 0;   // + s2d pack, conv1, pool1, soft-argmax
+  *launches = n > 0 ? int32_t(h->gemms.size()) + 3 : 0;   // + image pack, fused root, soft-argmax
   return METRO_OK;
 }
 
@@ -783,7 +746,8 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
       }
       if (!ctas) continue;
       acc[2] *= 2; acc[3] *= 2; acc[7] *= 2; acc[13] *= 2; acc[14] *= 2;        // MMA-thread columns exist in the pair leaders only
-      const std::string &nm = l == 0 ? h->root_gemm.name : h->gemms[l - 1].name;
+      if (l == 0) continue;
+      const std::string &nm = h->gemms[l - 1].name;
       fprintf(stderr, "%-28s %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %6.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f\n", nm.c_str(), acc[0] / ctas / 1e3,
               acc[1] / ctas / 1e3, acc[2] / ctas / 1e3, acc[3] / ctas / 1e3, acc[4] / ctas / 1e3, acc[5] / ctas / 1e3,
               acc[6] / ctas / 1e3, acc[7] / ctas, acc[8] / ctas / 1e3, acc[9] / ctas / 1e3, acc[10] / ctas / 1e3,

@@ -1,0 +1,377 @@
+// Root of the network in one kernel: conv1 7x7/2 + bias (resnet_v2.py:219-220, explicit pad (3,3) then
+// VALID, resnet_utils.py:124-135), pool1 3x3/2 with ZERO padding (resnet_v2.py:222-224,
+// resnet_utils.py:177-185: border maxima are clamped at >= 0) and the first unit's pre-activation
+// BN+ReLU (resnet_v2.py:119).  The 128x128x64 conv1 tensor (2 MB per crop) never reaches HBM.
+//
+// conv1 on the tensor core without an im2col expansion anywhere:
+//   * the image is re-packed once (img_pack_kernel) to fp16 "pixel pairs": P[n][h][q'][8] holds input
+//     columns (2q'-3, 2q'-2) x (r,g,b,0), q' in [0,132): 16 bytes per pair, zero pairs at both ends;
+//   * a tile is one conv1 output row (128 pixels = the UMMA M) of one crop.  Output pixel wo, kernel row
+//     kh reads pairs wo .. wo+3 of input row 2*ho+kh-3: for CONSECUTIVE wo these windows start 16 bytes
+//     apart, which is exactly the row pitch of the un-swizzled K-major UMMA operand layout
+//     ((8,m),(8,2)):((16 B, SBO),(2 B, LBO)) with SBO = 128 B and LBO = 16 B.  So the seven input rows are
+//     staged ONCE by one TMA box (14.8 KB) and 14 MMAs (7 kernel rows x 2 pair-pairs, K = 16 each) read
+//     overlapping windows of them straight from shared memory;
+//   * the packed weights (14 x [64 cout][16 k] fp16, zero for kw = 7 and the 4th channel) stay resident
+//     in shared memory for the whole kernel.
+// A CTA owns a band of pool rows of one crop and walks its conv rows top to bottom, keeping the last
+// three fp16 conv rows in shared memory; every second row it emits one pooled row (raw and pre-activated).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+#include "root_pool.h"
+
+namespace metro {
+
+namespace {
+
+constexpr int kSide = 256, kConvW = 128, kPoolW = 64, kC = 64;
+constexpr int kPairs = 132;                          // pairs per packed input row
+constexpr int kRowBytes = kPairs * 16;               // 2112
+constexpr int kStageRows = 7;
+constexpr int kStageBytes = 15360;                   // 7 * 2112 = 14784, padded to a multiple of 1 KB
+constexpr int kStages = 4;
+constexpr int kMmas = 14;                            // 7 kernel rows x 2 K=16 steps
+constexpr int kWBytes = kMmas * 2048;                // [mma][k-chunk 2][cout-group 8][8 rows][16 B]
+constexpr int kHistBytes = kConvW * 128;             // one fp16 conv row: 128 px x 64 ch
+constexpr int kThreads = 256;
+
+struct alignas(64) RootParams {
+  CUtensorMap pmap;        // P as [8 fp16][132 pairs][256 rows][n]
+  const __half *wpack;     // kWBytes, already in the shared-memory operand layout
+  const float *bias;       // [64] conv1 bias
+  const float *pscale, *pshift;   // [64] first unit's pre-activation
+  __half *raw, *pre;       // [n][64][64][64]; raw may be null
+  __half *conv_dbg;        // optional [n][128][128][64]: conv1 output (keep_activations)
+  int n, n_base, bands_per_img, pool_rows_per_band;   // crops n_base .. n_base + n of the buffers
+};
+
+constexpr int kOffW = kStages * kStageBytes;                 // 61440
+constexpr int kOffHist = kOffW + kWBytes;                    // 90112
+constexpr int kOffBias = kOffHist + 3 * kHistBytes;          // 139264
+constexpr int kOffBar = kOffBias + 256;
+constexpr int kSmemBytes = kOffBar + 128;
+
+// un-swizzled K-major operand: rows 16 B apart inside an 8-row core matrix, `sbo` between 8-row groups,
+// `lbo` between the two 8-element K chunks (cute/atom/mma_traits_sm100.hpp, LayoutType::INTERLEAVE)
+__device__ __forceinline__ uint64_t make_nosw_kmajor_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;                         // descriptor version (sm_100)
+  return d;                                       // layout type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_constant__ RootParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
+  uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = tfull + 2;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  float *s_bias = reinterpret_cast<float *>(smem + kOffBias);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_bands = p.n * p.bands_per_img;
+  const int PB = p.pool_rows_per_band;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&p.pmap);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(s_tmem, 128);
+    ptx::tmem_relinquish();
+  }
+  // resident weights (already in operand layout) and the bias
+  for (int i = threadIdx.x; i < kWBytes / 16; i += kThreads)
+    reinterpret_cast<uint4 *>(smem + kOffW)[i] = reinterpret_cast<const uint4 *>(p.wpack)[i];
+  if (threadIdx.x < kC) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  ptx::fence_proxy_async();                       // generic-proxy writes of the weights -> tensor-core reads
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  ptx::griddep_wait();                            // the packed image comes from the previous kernel
+  ptx::griddep_launch_dependents();
+
+  // conv rows of band b: r = 2*p0 - 1 .. 2*(p0 + PB) - 1 (row -1 = zero padding of the pool, not computed)
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
+        const int img = p.n_base + band / p.bands_per_img, p0 = (band % p.bands_per_img) * PB;
+        for (int r = max(2 * p0 - 1, 0); r <= 2 * (p0 + PB) - 1; ++r) {
+          ptx::mbar_wait(empty + stage, phase ^ 1);
+          ptx::mbar_arrive_expect_tx(full + stage, kStageRows * kRowBytes);
+          ptx::tma_load_4d(smem + stage * kStageBytes, &p.pmap, full + stage, 0, 0, 2 * r - 3, img);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(128, kC);
+      const uint32_t w_a = ptx::smem_u32(smem + kOffW);
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
+        const int p0 = (band % p.bands_per_img) * PB;
+        for (int r = max(2 * p0 - 1, 0); r <= 2 * (p0 + PB) - 1; ++r, ++it) {
+          const int acc = it & 1;
+          ptx::mbar_wait(tempty + acc, ((it >> 1) & 1) ^ 1);
+          ptx::mbar_wait(full + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(smem + stage * kStageBytes);
+#pragma unroll
+          for (int t = 0; t < kMmas; ++t) {
+            const int kh = t >> 1, jp = t & 1;
+            // A row m = output column wo: pairs wo + 2*jp, wo + 2*jp + 1 of packed input row kh
+            const uint64_t da = make_nosw_kmajor_desc(a0 + kh * kRowBytes + jp * 32, 16, 128);
+            const uint64_t db = make_nosw_kmajor_desc(w_a + t * 2048, 1024, 128);
+            ptx::umma_f16(tmem_base + acc * kC, da, db, idesc, t != 0);
+          }
+          ptx::umma_commit(empty + stage);
+          ptx::umma_commit(tfull + acc);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: thread = conv output column wo (TMEM lane) ----
+    const int q = warp - 4, et = threadIdx.x - 128;           // et = wo
+    const uint32_t hist_a = ptx::smem_u32(smem + kOffHist);
+    const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16);
+    // pooling role of this thread: channel chunk (8 channels) and pooled columns pw0 + 16 i
+    const int chunk = et & 7, pw0 = et >> 3;
+    float ps[8], pf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ps[i] = p.pscale[chunk * 8 + i]; pf[i] = p.pshift[chunk * 8 + i]; }
+    uint32_t it = 0;
+    for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
+      const int img = p.n_base + band / p.bands_per_img, p0 = (band % p.bands_per_img) * PB;
+      for (int r = 2 * p0 - 1; r <= 2 * (p0 + PB) - 1; ++r) {
+        const uint32_t slot = hist_a + uint32_t((r + 3) % 3) * kHistBytes + uint32_t(et) * 128u;
+        if (r < 0) {
+          // zero padding row above the image takes part in the max (Q6)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(slot + (uint32_t(j ^ (et & 7)) << 4)), "r"(0u) : "memory");
+          }
+        } else {
+          const int acc = it & 1;
+          ptx::mbar_wait(tfull + acc, (it >> 1) & 1);
+          ptx::tc_fence_after();
+          uint32_t v0[32], v1[32];
+          __syncwarp();
+          ptx::tmem_ld_32x32(taddr0 + acc * kC, v0);
+          ptx::tmem_ld_32x32(taddr0 + acc * kC + 32, v1);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty + acc);
+          ++it;
+          __half *dbg = p.conv_dbg ? p.conv_dbg + ((size_t(img) * kConvW + r) * kConvW + et) * kC : nullptr;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t *v = j < 4 ? v0 + 8 * j : v1 + 8 * (j - 4);
+            uint4 o;
+            o.x = pack2(__uint_as_float(v[0]) + s_bias[8 * j + 0], __uint_as_float(v[1]) + s_bias[8 * j + 1]);
+            o.y = pack2(__uint_as_float(v[2]) + s_bias[8 * j + 2], __uint_as_float(v[3]) + s_bias[8 * j + 3]);
+            o.z = pack2(__uint_as_float(v[4]) + s_bias[8 * j + 4], __uint_as_float(v[5]) + s_bias[8 * j + 5]);
+            o.w = pack2(__uint_as_float(v[6]) + s_bias[8 * j + 6], __uint_as_float(v[7]) + s_bias[8 * j + 7]);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t(j ^ (et & 7)) << 4)), "r"(o.x),
+                         "r"(o.y), "r"(o.z), "r"(o.w)
+                         : "memory");
+            if (dbg) reinterpret_cast<uint4 *>(dbg)[j] = o;
+          }
+        }
+        if (r >= 1 && (r & 1)) {
+          // rows r-2, r-1, r are in the history: pooled row pr = (r - 1) / 2
+          ptx::named_bar_sync(1, 128);
+          const int pr = (r - 1) >> 1;
+          const uint32_t s0 = hist_a + uint32_t((r + 1) % 3) * kHistBytes;   // (r - 2 + 3) % 3
+          const uint32_t s1 = hist_a + uint32_t((r + 2) % 3) * kHistBytes;
+          const uint32_t s2 = hist_a + uint32_t((r + 3) % 3) * kHistBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pw = pw0 + 16 * i;
+            __half2 m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m[k] = __floats2half2_rn(0.f, 0.f);   // column -1 is zero padding; also the
+            bool first = pw > 0;                                                // identity when the window is full
+#pragma unroll
+            for (int dc = -1; dc <= 1; ++dc) {
+              const int col = 2 * pw + dc;
+              if (col < 0) continue;
+              const uint32_t off = uint32_t(col) * 128u + (uint32_t(chunk ^ (col & 7)) << 4);
+#pragma unroll
+              for (int rr = 0; rr < 3; ++rr) {
+                const uint4 x = ptx::lds_v4u((rr == 0 ? s0 : rr == 1 ? s1 : s2) + off);
+                const __half2 *xh = reinterpret_cast<const __half2 *>(&x);
+                if (first) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) m[k] = xh[k];
+                  first = false;
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], xh[k]);
+                }
+              }
+            }
+            const size_t o = ((size_t(img) * kPoolW + pr) * kPoolW + pw) * kC + chunk * 8;
+            uint4 ro;
+            __half2 *rh = reinterpret_cast<__half2 *>(&ro);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rh[k] = m[k];
+            if (p.raw) *reinterpret_cast<uint4 *>(p.raw + o) = ro;
+            uint4 po;
+            uint32_t *pw32 = reinterpret_cast<uint32_t *>(&po);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 y = __half22float2(m[k]);
+              pw32[k] = pack2_relu(fmaf(y.x, ps[2 * k], pf[2 * k]), fmaf(y.y, ps[2 * k + 1], pf[2 * k + 1]));
+            }
+            *reinterpret_cast<uint4 *>(p.pre + o) = po;
+          }
+          ptx::named_bar_sync(1, 128);             // the oldest history row may be overwritten now
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// float32 / uint8 NHWC [n,256,256,3] -> fp16 pairs [n][256][132][8]; thread = one pair.  Values are rounded
+// to fp16 exactly like the reference's cast to FLAGS.dtype (architectures.py:29); the uint8 variant fuses the
+// /255 of improc.py:56-61.
+template <bool U8>
+__global__ void __launch_bounds__(256) img_pack_kernel(const void *__restrict__ img, __half *__restrict__ out, int n) {
+  const size_t total = size_t(n) * kSide * kPairs;
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = int(i % kPairs);
+  const size_t row = i / kPairs;                      // n * 256 + h
+  float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int col = 2 * q - 3 + e;
+    if (col < 0 || col >= kSide) continue;
+    const size_t base = (row * kSide + col) * 3;
+    if (U8) {
+      const unsigned char *s = static_cast<const unsigned char *>(img) + base;
+      for (int c = 0; c < 3; ++c) v[3 * e + c] = float(s[c]) * (1.0f / 255.0f);
+    } else {
+      const float *s = static_cast<const float *>(img) + base;
+      for (int c = 0; c < 3; ++c) v[3 * e + c] = s[c];
+    }
+  }
+  uint4 o;
+  o.x = pack2(v[0], v[1]); o.y = pack2(v[2], 0.f); o.z = pack2(v[3], v[4]); o.w = pack2(v[5], 0.f);
+  reinterpret_cast<uint4 *>(out)[i] = o;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+size_t root_packed_image_elems() { return size_t(kSide) * kPairs * 8; }
+size_t root_packed_weight_elems() { return kWBytes / 2; }
+
+void root_pack_weights(const float *w_hwio, __half *dst) {
+  // HWIO [7][7][3][64] -> 14 x [k-chunk 2][cout-group 8][8 rows][8 k] fp16 (un-swizzled K-major operand):
+  // MMA t = 2*kh + jp, k = 16 values = pairs (2jp, 2jp+1) x (2 pixels) x (r,g,b,0): kw = 2*(2jp + k/8) + (k/4)%2
+  for (size_t i = 0; i < size_t(kWBytes / 2); ++i) dst[i] = __float2half_rn(0.f);
+  for (int t = 0; t < kMmas; ++t) {
+    const int kh = t >> 1, jp = t & 1;
+    for (int k = 0; k < 16; ++k) {
+      const int kw = 2 * (2 * jp + (k >> 3)) + ((k >> 2) & 1), ch = k & 3;
+      if (kw > 6 || ch > 2) continue;
+      for (int o = 0; o < kC; ++o)
+        dst[size_t(t) * 1024 + (k >> 3) * 512 + (o >> 3) * 64 + (o & 7) * 8 + (k & 7)] =
+            __float2half_rn(w_hwio[((size_t(kh) * 7 + kw) * 3 + ch) * kC + o]);
+    }
+  }
+}
+
+metro_status root_make_image_map(void *map_out, const __half *packed, int n) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  const cuuint64_t dims[4] = {8, cuuint64_t(kPairs), cuuint64_t(kSide), cuuint64_t(n)};
+  const cuuint64_t strides[3] = {16, cuuint64_t(kRowBytes), cuuint64_t(kRowBytes) * kSide};
+  const cuuint32_t box[4] = {8, cuuint32_t(kPairs), cuuint32_t(kStageRows), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(static_cast<CUtensorMap *>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(packed),
+                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled(packed image, n=%d) -> %d", n, int(r));
+  return METRO_OK;
+}
+
+metro_status img_pack_launch(const void *img, bool u8, __half *out, int n, cudaStream_t stream) {
+  if (n == 0) return METRO_OK;
+  const size_t total = size_t(n) * kSide * kPairs;
+  const unsigned blocks = unsigned((total + 255) / 256);
+  if (u8) img_pack_kernel<true><<<blocks, 256, 0, stream>>>(img, out, n);
+  else img_pack_kernel<false><<<blocks, 256, 0, stream>>>(img, out, n);
+  METRO_CUDA(cudaGetLastError());
+  return METRO_OK;
+}
+
+metro_status root_fused_launch(const void *image_map, const __half *wpack, const float *bias, const float *pscale,
+                               const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base,
+                               int num_sms, cudaStream_t stream) {
+  if (n == 0) return METRO_OK;
+  static bool configured = false;
+  if (!configured) {
+    METRO_CUDA(cudaFuncSetAttribute(root_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  RootParams p;
+  p.pmap = *static_cast<const CUtensorMap *>(image_map);
+  p.wpack = wpack; p.bias = bias; p.pscale = pscale; p.pshift = pshift;
+  p.raw = raw; p.pre = pre; p.conv_dbg = conv_dbg;
+  p.n = n; p.n_base = n_base; p.pool_rows_per_band = 8; p.bands_per_img = kPoolW / 8;
+  const int n_bands = n * p.bands_per_img;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(n_bands < num_sms ? n_bands : num_sms)); cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  METRO_CUDA(cudaLaunchKernelEx(&cfg, root_fused_kernel, p));
+  return METRO_OK;
+}
+
+}  // namespace metro
