@@ -21,6 +21,7 @@
 //     normalisation pass ever touches HBM.  The projection shortcut (resnet_v2.py:123-125) is a
 //     second A source accumulated into the same TMEM tile (K concatenation).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -559,7 +560,8 @@ metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream)
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("METRO_NO_PDL") != nullptr;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
   METRO_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kMode, kXform>, L.prm));
   return METRO_OK;
 }

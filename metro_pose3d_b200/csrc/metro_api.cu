@@ -330,7 +330,8 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     // applies its own pre-activation inside conv1 (conv_gemm kXform), so the previous unit's conv3 writes one
     // tensor instead of two.  Same arithmetic and rounding as the stored pre-activation, hence bit-identical.
     auto reads_raw = [&](size_t k) {
-      return !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= 256;
+      static const bool no_xform = getenv("METRO_NO_XFORM") != nullptr;
+      return !no_xform && !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= 256;
     };
     // conv1: 1x1, BN, ReLU on the pre-activation (resnet_v2.py:127-128)
     {

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"
@@ -202,8 +203,9 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
             if (dbg) reinterpret_cast<uint4 *>(dbg)[j] = o;
           }
         }
-        if (r >= 1 && (r & 1)) {
-          // rows r-2, r-1, r are in the history: pooled row pr = (r - 1) / 2
+        if ((r & 1) && r > 2 * p0 - 1) {
+          // rows r-2, r-1, r of THIS band are in the history (the band's first row 2*p0-1 is only a halo):
+          // pooled row pr = (r - 1) / 2
           ptx::named_bar_sync(1, 128);
           const int pr = (r - 1) >> 1;
           const uint32_t s0 = hist_a + uint32_t((r + 1) % 3) * kHistBytes;   // (r - 2 + 3) % 3
@@ -369,7 +371,8 @@ metro_status root_fused_launch(const void *image_map, const __half *wpack, const
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("METRO_NO_PDL") != nullptr;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
   METRO_CUDA(cudaLaunchKernelEx(&cfg, root_fused_kernel, p));
   return METRO_OK;
 }
