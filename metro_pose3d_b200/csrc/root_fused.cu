@@ -39,7 +39,7 @@ constexpr int kStages = 4;
 constexpr int kMmas = 14;                            // 7 kernel rows x 2 K=16 steps
 constexpr int kWBytes = kMmas * 2048;                // [mma][k-chunk 2][cout-group 8][8 rows][16 B]
 constexpr int kHistBytes = kConvW * 128;             // one fp16 conv row: 128 px x 64 ch
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;                        // 4 control warps + 8 epilogue warps (2 per TMEM lane quarter)
 
 struct alignas(64) RootParams {
   CUtensorMap pmap;        // P as [8 fp16][132 pairs][256 rows][n]
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
   if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&p.pmap);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 8); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -155,11 +155,13 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ---- epilogue: thread = conv output column wo (TMEM lane) ----
-    const int q = warp - 4, et = threadIdx.x - 128;           // et = wo
+    // ---- epilogue: thread = (conv output column wo = TMEM lane, half of the 64 channels) ----
+    const int e = warp - 4, q = e & 3, hf = e >> 2;           // q == warp % 4: the TMEM lane quarter
+    const int wo = q * 32 + lane;
+    const int et = threadIdx.x - 128;                         // 0..255
     const uint32_t hist_a = ptx::smem_u32(smem + kOffHist);
-    const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16);
-    // pooling role of this thread: channel chunk (8 channels) and pooled columns pw0 + 16 i
+    const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + hf * 32;
+    // pooling role of this thread: channel chunk (8 channels) and pooled columns pw0 + 32 i
     const int chunk = et & 7, pw0 = et >> 3;
     float ps[8], pf[8];
 #pragma unroll
@@ -168,37 +170,37 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
     for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
       const int img = p.n_base + band / p.bands_per_img, p0 = (band % p.bands_per_img) * PB;
       for (int r = 2 * p0 - 1; r <= 2 * (p0 + PB) - 1; ++r) {
-        const uint32_t slot = hist_a + uint32_t((r + 3) % 3) * kHistBytes + uint32_t(et) * 128u;
+        const uint32_t slot = hist_a + uint32_t((r + 3) % 3) * kHistBytes + uint32_t(wo) * 128u;
         if (r < 0) {
           // zero padding row above the image takes part in the max (Q6)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(slot + (uint32_t(j ^ (et & 7)) << 4)), "r"(0u) : "memory");
+          for (int j = 0; j < 4; ++j) {
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)), "r"(0u) : "memory");
           }
         } else {
           const int acc = it & 1;
           ptx::mbar_wait(tfull + acc, (it >> 1) & 1);
           ptx::tc_fence_after();
-          uint32_t v0[32], v1[32];
+          uint32_t v[32];
           __syncwarp();
-          ptx::tmem_ld_32x32(taddr0 + acc * kC, v0);
-          ptx::tmem_ld_32x32(taddr0 + acc * kC + 32, v1);
+          ptx::tmem_ld_32x32(taddr0 + acc * kC, v);
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tempty + acc);
           ++it;
-          __half *dbg = p.conv_dbg ? p.conv_dbg + ((size_t(img) * kConvW + r) * kConvW + et) * kC : nullptr;
+          __half *dbg = p.conv_dbg ? p.conv_dbg + ((size_t(img) * kConvW + r) * kConvW + wo) * kC + hf * 32 : nullptr;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t *v = j < 4 ? v0 + 8 * j : v1 + 8 * (j - 4);
+          for (int j = 0; j < 4; ++j) {
+            const float *b = s_bias + hf * 32 + 8 * j;
+            const float4 b0 = *reinterpret_cast<const float4 *>(b), b1 = *reinterpret_cast<const float4 *>(b + 4);
             uint4 o;
-            o.x = pack2(__uint_as_float(v[0]) + s_bias[8 * j + 0], __uint_as_float(v[1]) + s_bias[8 * j + 1]);
-            o.y = pack2(__uint_as_float(v[2]) + s_bias[8 * j + 2], __uint_as_float(v[3]) + s_bias[8 * j + 3]);
-            o.z = pack2(__uint_as_float(v[4]) + s_bias[8 * j + 4], __uint_as_float(v[5]) + s_bias[8 * j + 5]);
-            o.w = pack2(__uint_as_float(v[6]) + s_bias[8 * j + 6], __uint_as_float(v[7]) + s_bias[8 * j + 7]);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t(j ^ (et & 7)) << 4)), "r"(o.x),
-                         "r"(o.y), "r"(o.z), "r"(o.w)
+            o.x = pack2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
+            o.y = pack2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
+            o.z = pack2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
+            o.w = pack2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)),
+                         "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
                          : "memory");
             if (dbg) reinterpret_cast<uint4 *>(dbg)[j] = o;
           }
@@ -206,14 +208,14 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
         if ((r & 1) && r > 2 * p0 - 1) {
           // rows r-2, r-1, r of THIS band are in the history (the band's first row 2*p0-1 is only a halo):
           // pooled row pr = (r - 1) / 2
-          ptx::named_bar_sync(1, 128);
+          ptx::named_bar_sync(1, 256);
           const int pr = (r - 1) >> 1;
           const uint32_t s0 = hist_a + uint32_t((r + 1) % 3) * kHistBytes;   // (r - 2 + 3) % 3
           const uint32_t s1 = hist_a + uint32_t((r + 2) % 3) * kHistBytes;
           const uint32_t s2 = hist_a + uint32_t((r + 3) % 3) * kHistBytes;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int pw = pw0 + 16 * i;
+          for (int i = 0; i < 2; ++i) {
+            const int pw = pw0 + 32 * i;
             __half2 m[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) m[k] = __floats2half2_rn(0.f, 0.f);   // column -1 is zero padding; also the
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
             }
             *reinterpret_cast<uint4 *>(p.pre + o) = po;
           }
-          ptx::named_bar_sync(1, 128);             // the oldest history row may be overwritten now
+          ptx::named_bar_sync(1, 256);             // the oldest history row may be overwritten now
         }
       }
     }

@@ -103,6 +103,23 @@ def test_sliced_host_path_equals_device_path():
     assert np.isfinite(a).all() and np.abs(a).max() > 1.0
 
 
+def test_large_batch_matches_small_batches():
+    """A crop's result must not depend on the batch it is part of, in particular not on where the persistent
+    kernels' work lists wrap around the grid (148 CTAs / 74 CTA pairs): 160 crops in one call vs the same crops
+    in calls of 8, bit for bit, and run-to-run determinism."""
+    import torch
+    from metro_pose3d_b200.inference import MetroModel
+    n = 160
+    model = MetroModel('resnet_v2_50', 16, 'h36m', max_batch=n)
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand((n, 256, 256, 3), generator=g, dtype=torch.float32).cuda()
+    full = model.infer(img).cpu().numpy()
+    assert np.array_equal(full, model.infer(img).cpu().numpy())
+    for lo in (0, 16, 72, 144, 152):
+        part = model.infer(img[lo:lo + 8].contiguous()).cpu().numpy()
+        assert np.array_equal(part, full[lo:lo + 8]), f'crops {lo}..{lo + 8} depend on their batch'
+
+
 def test_in_kernel_preactivation_is_bit_identical():
     """Production handles let identity units of block1/2 read their raw input and apply the pre-activation
     inside conv1 (no stored pre-activation tensor); keep_activations handles store every tensor.  Same
