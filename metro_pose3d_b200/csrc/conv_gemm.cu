@@ -568,24 +568,6 @@ metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream)
 
 }  // namespace
 
-metro_status make_tensor_map_4d(CUtensorMap *map, const void *base, const unsigned long long dims_[4],
-                                const unsigned long long strides_[3], const unsigned box_[4]) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[4], strides[3];
-  cuuint32_t box[4];
-  for (int i = 0; i < 4; ++i) { dims[i] = dims_[i]; box[i] = box_[i]; }
-  for (int i = 0; i < 3; ++i) strides[i] = strides_[i];
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled(4d dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu) -> %d", dims_[0],
-                dims_[1], dims_[2], dims_[3], strides_[0], strides_[1], strides_[2], int(r));
-  return METRO_OK;
-}
-
 metro_status make_out_tensor_map(CUtensorMap *map, const void *base, long long m_rows, int cout) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");

@@ -55,8 +55,6 @@ struct ConvGemmLaunch {
 };
 
 // Tensor-map helpers (driver entry point resolved at run time; no link-time libcuda dependency).
-metro_status make_tensor_map_4d(CUtensorMap *map, const void *base, const unsigned long long dims[4],
-                                const unsigned long long strides_bytes[3], const unsigned box[4]);
 metro_status make_act_tensor_map(CUtensorMap *map, const void *base, int n, int h, int w, int c,
                                  int sub, int ph, int pw, int box_w, int box_h, int box_n);
 metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout_pad, int k_total, int block_n);

@@ -10,7 +10,7 @@
 #include "common.h"
 #include "conv_gemm.h"
 #include "plan.h"
-#include "root_pool.h"
+#include "root_fused.h"
 
 namespace metro {
 
@@ -81,13 +81,6 @@ struct GemmSpec {
   const __half *src = nullptr; int in_side = 0, cin = 0;
   int k = 1, stride = 1, rate = 1, pad_lo = 0, out_side = 0, cout = 0;
   const float *w = nullptr;                 // host HWIO
-  const __half *w_packed_host = nullptr;    // alternative: already packed [cout_pad][K] (root conv)
-  int k_packed = 0;
-  // custom source-0 view (root conv on the space-to-depth image): explicit 4-D tensor map + row taps
-  bool custom_a = false;
-  int c_taps = 0;
-  unsigned long long c_dims[4] = {0, 0, 0, 0}, c_strides[3] = {0, 0, 0};
-  unsigned c_box[4] = {0, 0, 0, 0};
   const __half *src2 = nullptr; int cin2 = 0; const float *w2 = nullptr;
   std::vector<float> scale, shift, scale2, shift2;
   std::vector<float> ascale, ashift;        // optional pre-activation applied to source 0 inside the kernel (1x1 only)
@@ -122,32 +115,21 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   if (st != METRO_OK) return st;
   int K;
   std::vector<__half> packed;
-  if (g.custom_a) {
-    p.taps = g.c_taps; p.cblk0 = 1; p.cblk1 = 0;
-    for (int t = 0; t < g.c_taps; ++t) { p.tap_map[t] = 0; p.tap_dh[t] = (signed char)t; p.tap_dw[t] = 0; }
-    K = g.k_packed;
-    packed.assign(size_t(cout_pad) * K, __float2half_rn(0.f));
-    std::memcpy(packed.data(), g.w_packed_host, size_t(g.cout) * K * sizeof(__half));
-  } else {
-    st = conv_gemm_set_taps(p, g.k, g.stride, g.rate, g.pad_lo);
-    if (st != METRO_OK) return st;
-    p.cblk0 = g.cin / kTileK;
-    p.cblk1 = (g.cin2 + res_c) / kTileK;
-    p.diag2 = g.res ? 1 : 0;
-    K = g.k * g.k * g.cin + g.cin2 + res_c;
-    packed.resize(size_t(cout_pad) * K);
-    conv_gemm_pack_weights(g.w, g.k, g.cin, g.cout, g.res ? nullptr : g.w2, g.cin2 + res_c, cout_pad, packed.data());
-  }
+  st = conv_gemm_set_taps(p, g.k, g.stride, g.rate, g.pad_lo);
+  if (st != METRO_OK) return st;
+  p.cblk0 = g.cin / kTileK;
+  p.cblk1 = (g.cin2 + res_c) / kTileK;
+  p.diag2 = g.res ? 1 : 0;
+  K = g.k * g.k * g.cin + g.cin2 + res_c;
+  packed.resize(size_t(cout_pad) * K);
+  conv_gemm_pack_weights(g.w, g.k, g.cin, g.cout, g.res ? nullptr : g.w2, g.cin2 + res_c, cout_pad, packed.data());
   __half *d_w = nullptr;
   st = arena.upload(&d_w, packed);
   if (st != METRO_OK) return st;
   st = make_weight_tensor_map(&p.bmap, d_w, cout_pad, K, L.block_n);
   if (st != METRO_OK) return st;
   // activations
-  if (g.custom_a) {
-    st = make_tensor_map_4d(&p.amap[0], g.src, g.c_dims, g.c_strides, g.c_box);
-    if (st != METRO_OK) return st;
-  } else if (g.stride == 1) {
+  if (g.stride == 1) {
     st = make_act_tensor_map(&p.amap[0], g.src, g.n_max, g.in_side, g.in_side, g.cin, 1, 0, 0, p.wo, p.th, p.nb);
     if (st != METRO_OK) return st;
   } else {
@@ -176,7 +158,7 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
     st = arena.upload(&d, g.shift2, cout_pad); if (st != METRO_OK) return st; p.shift2 = d;
   }
   if (!g.ascale.empty()) {
-    if (g.k != 1 || g.stride != 1 || g.cin2 || g.res || g.out2 || L.direct || L.block_n > 256 || g.custom_a)
+    if (g.k != 1 || g.stride != 1 || g.cin2 || g.res || g.out2 || L.direct || L.block_n > 256)
       return fail(METRO_ERR_VALUE, "%s: the in-kernel pre-activation needs a plain 1x1 convolution with <= 128 outputs", g.name.c_str());
     st = arena.upload(&d, g.ascale); if (st != METRO_OK) return st; p.ascale = d;
     st = arena.upload(&d, g.ashift); if (st != METRO_OK) return st; p.ashift = d;

@@ -24,7 +24,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
-#include "root_pool.h"
+#include "root_fused.h"
 
 namespace metro {
 
