@@ -152,11 +152,17 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 192 ? 3 : 1) softargmax_kernel(c
   if (tid == 0) {
     for (int st = 0; st < kStages; ++st) ptx::mbar_init(full + st, 1);
     ptx::fence_mbar_init();
-    for (int st = 0; st < kStages && !prod.done(n_items); ++st) { issue(prod, st); advance(prod); }
   }
   for (int q = tid; q < p.ppc; q += nthreads) {
     const int h = q / p.W;
     s_hw[q] = make_float2(float(h), float(q - h * p.W));
+  }
+  // programmatic dependent launch: the set-up above overlaps the tail of the kernel that produces the head
+  // tensor (the logits convolution); nothing before this line touches global memory
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
+  if (tid == 0) {
+    for (int st = 0; st < kStages && !prod.done(n_items); ++st) { issue(prod, st); advance(prod); }
   }
   __syncthreads();                       // barriers initialised and the (row, column) table written
 
@@ -369,8 +375,13 @@ metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
   }
   const int n_items = L.n * L.splits;
   const dim3 grid(unsigned(n_items < L.max_ctas ? n_items : L.max_ctas)), block(unsigned((L.slots * L.lanes + 31) & ~31));
-  softargmax_kernel<VEC, LANES, F16, MAXT><<<grid, block, sm, stream>>>(L);
-  METRO_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = sm; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  METRO_CUDA(cudaLaunchKernelEx(&cfg, softargmax_kernel<VEC, LANES, F16, MAXT>, L));
   return METRO_OK;
 }
 
