@@ -60,7 +60,7 @@ metro_status make_act_tensor_map(CUtensorMap *map, const void *base, int n, int 
 metro_status make_weight_tensor_map(CUtensorMap *map, const void *base, int cout_pad, int k_total, int block_n);
 metro_status make_out_tensor_map(CUtensorMap *map, const void *base, long long m_rows, int cout);
 
-int conv_gemm_pick_block_n(int cout, bool direct);
+int conv_gemm_pick_block_n(int cout, bool direct, long long m_rows);
 int conv_gemm_cout_pad(int cout, int block_n);
 // Lays out shared memory (stage count, staging buffers) once block_n and the has_* flags are set.
 metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks);

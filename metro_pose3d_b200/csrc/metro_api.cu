@@ -100,7 +100,7 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   ConvGemmParams &p = L.prm;
   std::memset(&p, 0, sizeof p);
   L.direct = g.out1_f32 || (g.cout % 64 != 0);   // the logits head (136 / 152 channels, fp32 or fp16)
-  L.block_n = conv_gemm_pick_block_n(g.cout, L.direct);
+  L.block_n = conv_gemm_pick_block_n(g.cout, L.direct, (long long)g.n_max * g.out_side * g.out_side);
   if (L.direct && (g.out2 || g.res)) return fail(METRO_ERR_VALUE, "%s: this output shape excludes a residual / second output", g.name.c_str());
   if (g.res && g.cin2) return fail(METRO_ERR_VALUE, "%s: identity and projection shortcuts are exclusive", g.name.c_str());
   if (g.res) {
