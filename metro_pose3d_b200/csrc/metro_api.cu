@@ -205,6 +205,7 @@ struct metro_handle {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   float *stage_img = nullptr, *stage_pose = nullptr;
   int host_chunk = 64;    // crops per PCIe slice of metro_infer_host (METRO_HOST_CHUNK)
+  int host_tail = 128;    // crops per slice of the deep blocks (METRO_HOST_TAIL; 0 = whole batch)
   int stem_gemms = 0;     // tensor-core convolutions that run per slice (up to the last 32x32-or-larger block)
 };
 
@@ -366,6 +367,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     cur_raw = nraw; cur_pre = npre;
   }
   if (const char *e = getenv("METRO_HOST_CHUNK")) h.host_chunk = atoi(e);
+  if (const char *e = getenv("METRO_HOST_TAIL")) h.host_tail = atoi(e);
   // ---- logits (resnet_v2.py:234-236) -> head tensor ----
   {
     const size_t eh = size_t(pl.feat_side) * pl.feat_side * pl.logits.cout;
@@ -429,8 +431,9 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
   return METRO_OK;
 }
 
-// The remaining convolutions, the logits head and the soft-argmax for crops [0, n).
-metro_status run_tail(metro_handle *h, int n, int first_gemm, float *poses, cudaStream_t s, Timer *t) {
+// The remaining convolutions, the logits head and the soft-argmax for crops [n_base, n_base + n); `poses`
+// points at crop 0 of the output.
+metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float *poses, cudaStream_t s, Timer *t) {
   metro_status st;
   auto mark = [&](const char *name) {
     if (!t) return;
@@ -439,16 +442,20 @@ metro_status run_tail(metro_handle *h, int n, int first_gemm, float *poses, cuda
   };
   for (size_t li = first_gemm; li < h->gemms.size(); ++li) {
     ConvGemmLaunch &L = h->gemms[li];
-    conv_gemm_set_batch(L.prm, n, 0);
+    conv_gemm_set_batch(L.prm, n, n_base);
     L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
   SoftargmaxLaunch sl = h->sam;
-  sl.n = n; sl.head = h->buf_head; sl.out = poses;
-  sl.counters = static_cast<unsigned int *>(h->sam_ws);
+  const size_t head_bytes = size_t(sl.H) * sl.W * sl.C * (sl.head_f16 ? 2 : 4);
+  sl.n = n;
+  sl.head = static_cast<const unsigned char *>(h->buf_head) + size_t(n_base) * head_bytes;
+  sl.out = poses + size_t(n_base) * sl.n_out * 3;
+  sl.counters = static_cast<unsigned int *>(h->sam_ws) + n_base;
   sl.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(h->sam_ws) +
-                                           ((size_t(h->max_batch) * 4 + 255) & ~size_t(255)));
+                                           ((size_t(h->max_batch) * 4 + 255) & ~size_t(255))) +
+                size_t(n_base) * sl.splits * sl.J * 5;
   if ((st = softargmax_launch(sl, s)) != METRO_OK) return st;
   mark("softargmax");
   return METRO_OK;
@@ -466,7 +473,7 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
   }
   metro_status st = run_stem(h, images, u8, n, 0, 0, s, t);
   if (st != METRO_OK) return st;
-  return run_tail(h, n, 0, poses, s, t);
+  return run_tail(h, n, 0, 0, poses, s, t);
 }
 
 }  // namespace
@@ -584,18 +591,26 @@ metro_status metro_infer_host(metro_handle *h, const float *images_host, int32_t
   int chunk = h->host_chunk;
   if (chunk <= 0 || chunk >= n) chunk = n;
   const int stem_gemms = chunk < n ? h->stem_gemms : 0;
-  int i = 0;
+  // the deep blocks follow in slices of `tail` crops (a multiple of the stem slice, 128 by default): the first
+  // half of the batch is finished while the second half is still crossing PCIe
+  int tail = h->host_tail > 0 ? (h->host_tail + chunk - 1) / chunk * chunk : n;
+  if (chunk == n) tail = n;
+  int i = 0, tail_lo = 0;
   for (int lo = 0; lo < n; lo += chunk, ++i) {
     const int cnt = lo + chunk <= n ? chunk : n - lo;
     METRO_CUDA(cudaMemcpyAsync(h->stage_img + size_t(lo) * img_elems, images_host + size_t(lo) * img_elems, img_bytes * cnt,
                                cudaMemcpyHostToDevice, h->copy_stream));
     METRO_CUDA(cudaEventRecord(h->ev_copied[i & 1], h->copy_stream));
     METRO_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied[i & 1], 0));
-    const metro_status st = run_stem(h, h->stage_img + size_t(lo) * img_elems, false, cnt, lo, stem_gemms, h->stream, nullptr);
+    metro_status st = run_stem(h, h->stage_img + size_t(lo) * img_elems, false, cnt, lo, stem_gemms, h->stream, nullptr);
     if (st != METRO_OK) return st;
+    const int done = lo + cnt;
+    if (done - tail_lo >= tail || done == n) {
+      st = run_tail(h, done - tail_lo, tail_lo, stem_gemms, h->stage_pose, h->stream, nullptr);
+      if (st != METRO_OK) return st;
+      tail_lo = done;
+    }
   }
-  const metro_status st = run_tail(h, n, stem_gemms, h->stage_pose, h->stream, nullptr);
-  if (st != METRO_OK) return st;
   METRO_CUDA(cudaMemcpyAsync(poses_host, h->stage_pose, pose_bytes * n, cudaMemcpyDeviceToHost, h->stream));
   METRO_CUDA(cudaStreamSynchronize(h->stream));
   return METRO_OK;
