@@ -278,9 +278,18 @@ def main():
     # algorithmic FLOPs: 2*Ho*Wo*Cout*Cin*k^2 per conv per crop; the root conv1 has its own fused kernel
     gemm_flops = sum(c.flops for c in gemm_convs) * n
     achieved_tf = gemm_flops / (conv_ms * 1e-3) / 1e12
+    # DRAM traffic of the same launches from the committed ncu capture (profiles/traffic_<config>.json), per step
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', f'traffic_{args.config}.json')
+    if os.path.exists(tpath) and n == cfg_batch // max(cfg_gpus, 1):
+        try:
+            traffic = json.load(open(tpath)).get('conv_gemm_dram_bytes_per_step')
+        except Exception:
+            traffic = None
     roofline = {'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all %d launches)' % len([k for k in acc if k not in non_gemm]),
                 'bound': 'tensor', 'achieved': achieved_tf, 'peak': tf_sust, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / tf_sust, 'traffic': None, 'peak_source': f'{peak_src} bf16 sustained',
+                'frac': achieved_tf / tf_sust, 'traffic': traffic, 'peak_source': f'{peak_src} bf16 sustained',
+                'algorithmic_flops_per_step': gemm_flops,
                 'ms_per_step': conv_ms, 'other_ms': {k: acc[k] for k in non_gemm if k in acc}}
     if args.layers:
         flops = {c.name: c.flops for c in spec.convs}

@@ -1,14 +1,17 @@
 """CPU oracle: a restatement of the reference's exported inference graph.  TEST INFRASTRUCTURE.
 
-    *** PARITY UNPINNED ***  The reference holds no tests, golden vectors, fixtures or weights
-     and its own implementation needs TensorFlow 1.13.1 +
-    tf.contrib.slim, which cannot be installed here (no wheel, no network, no py3.12 build).
-    The arithmetic lives in the third-party TensorFlow 1.13.1 op kernels (pinned at
-    install_dependencies.sh:13), so this file restates the *published semantics* of those ops
-    (SAME/VALID padding, HWIO filters, FusedBatchNorm inference form, reduce_max/exp/sum softmax,
-    linspace grids) at the reference's own call sites, cited line by line below.  It is pinned
-    only against self-derived analytic known answers (tests/test_oracle_*.py) and against an
-    independent scalar numpy convolution (tests/test_oracle_backbone.py).
+    PIN STATUS: pinned at graph level against the reference's own code run here; the TensorFlow 1.13.1
+    op kernels themselves are unpinned.  The reference holds no tests, golden vectors, fixtures or weights
+     and its own implementation needs TensorFlow 1.13.1 + tf.contrib.slim,
+    which cannot be installed here (no wheel, no network, no py3.12 build).  oracle/gen_golden.py
+    therefore imports the reference's Python files from /root/reference/src and executes them eagerly in
+    float64 over oracle/tf_shim.py; the outputs are committed under tests/golden/ and this module is
+    checked against them (tests/test_golden.py).  Every graph-level decision is thus the reference's;
+    the primitive op semantics (SAME/VALID padding, HWIO filters, FusedBatchNorm inference form,
+    reduce_max/exp/sum softmax, linspace grids) are restated from TensorFlow's documentation at the
+    reference's call sites, cited line by line below, and additionally checked against self-derived
+    analytic known answers (tests/test_oracle_*.py) and an independent scalar numpy convolution
+    (tests/test_oracle_backbone.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.  The product path (metro_pose3d_b200/) never does.
