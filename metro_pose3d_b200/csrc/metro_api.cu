@@ -419,7 +419,8 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
   if ((st = img_pack_launch(images, u8, h->buf_packed + size_t(n_base) * root_packed_image_elems(), n, s)) != METRO_OK) return st;
   mark("img_pack");
   if ((st = root_fused_launch(h->image_map, h->d_root_w, h->d_root_bias, h->d_pool_scale, h->d_pool_shift,
-                              h->spec.keep_activations ? h->pool_raw : nullptr, h->pool_pre, h->buf_root, n, n_base, h->num_sms, s)) != METRO_OK) return st;
+                              h->spec.keep_activations ? h->pool_raw : nullptr, h->pool_pre, h->buf_root, n, n_base, h->num_sms, s,
+                              (t && t->role_prof) ? t->role_prof : nullptr)) != METRO_OK) return st;
   mark("conv1+pool1");
   for (int li = 0; li < stem_gemms; ++li) {
     ConvGemmLaunch &L = h->gemms[li];
@@ -744,7 +745,20 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
       }
       if (!ctas) continue;
       acc[2] *= 2; acc[3] *= 2; acc[7] *= 2; acc[13] *= 2; acc[14] *= 2;        // MMA-thread columns exist in the pair leaders only
-      if (l == 0) continue;
+      if (l == 0) {   // fused root: producer total / wait-empty, MMA total / wait-acc / wait-full / rows, epilogue total / wait-acc
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int ctas = 0;
+        for (int c = 0; c < h->num_sms; ++c) {
+          const long long *r = &host[size_t(c) * 8];
+          if (r[2] == 0) continue;
+          ++ctas;
+          for (int k = 0; k < 8; ++k) a[k] += double(r[k]);
+        }
+        if (ctas)
+          fprintf(stderr, "root_fused (kcycles): prod total %.1f wait_empty %.1f | mma total %.1f wait_acc %.1f wait_full %.1f rows %.1f | epi total %.1f wait_acc %.1f\n",
+                  a[0] / ctas / 1e3, a[1] / ctas / 1e3, a[2] / ctas / 1e3, a[3] / ctas / 1e3, a[4] / ctas / 1e3, a[5] / ctas, a[6] / ctas / 1e3, a[7] / ctas / 1e3);
+        continue;
+      }
       const std::string &nm = h->gemms[l - 1].name;
       fprintf(stderr, "%-28s %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f %6.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f %8.1f\n", nm.c_str(), acc[0] / ctas / 1e3,
               acc[1] / ctas / 1e3, acc[2] / ctas / 1e3, acc[3] / ctas / 1e3, acc[4] / ctas / 1e3, acc[5] / ctas / 1e3,

@@ -14,8 +14,10 @@
 //     overlapping windows of them straight from shared memory;
 //   * the packed weights (14 x [64 cout][16 k] fp16, zero for kw = 7 and the 4th channel) stay resident
 //     in shared memory for the whole kernel.
-// A CTA owns a band of pool rows of one crop and walks its conv rows top to bottom, keeping the last
-// three fp16 conv rows in shared memory; every second row it emits one pooled row (raw and pre-activated).
+// A CTA owns a band of pool rows of one crop and walks its conv rows top to bottom; the pool is separable:
+// each epilogue thread keeps the previous two rows of its own column in registers and writes the vertical
+// maximum of three rows to shared memory every second row, from which the pooled row (raw and pre-activated)
+// is the horizontal stride-2 maximum.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -42,18 +44,19 @@ constexpr int kHistBytes = kConvW * 128;             // one fp16 conv row: 128 p
 constexpr int kThreads = 384;                        // 4 control warps + 8 epilogue warps (2 per TMEM lane quarter)
 
 struct alignas(64) RootParams {
-  CUtensorMap pmap;        // P as [8 fp16][132 pairs][256 rows][n]
+  CUtensorMap pmap;        // P as [176 fp16][6 segments][256 rows][n] (a row = 132 pairs x 8 fp16)
   const __half *wpack;     // kWBytes, already in the shared-memory operand layout
   const float *bias;       // [64] conv1 bias
   const float *pscale, *pshift;   // [64] first unit's pre-activation
   __half *raw, *pre;       // [n][64][64][64]; raw may be null
   __half *conv_dbg;        // optional [n][128][128][64]: conv1 output (keep_activations)
   int n, n_base, bands_per_img, pool_rows_per_band;   // crops n_base .. n_base + n of the buffers
+  long long *prof;         // optional [grid][8] role timers (cycles)
 };
 
 constexpr int kOffW = kStages * kStageBytes;                 // 61440
 constexpr int kOffHist = kOffW + kWBytes;                    // 90112
-constexpr int kOffBias = kOffHist + 3 * kHistBytes;          // 139264
+constexpr int kOffBias = kOffHist + 2 * kHistBytes;          // two slots of column-wise maxima
 constexpr int kOffBar = kOffBias + 256;
 constexpr int kSmemBytes = kOffBar + 128;
 
@@ -116,70 +119,91 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      long long tw = 0;
+      const long long tstart = clock64();
       for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
         const int img = p.n_base + band / p.bands_per_img, p0 = (band % p.bands_per_img) * PB;
         for (int r = max(2 * p0 - 1, 0); r <= 2 * (p0 + PB) - 1; ++r) {
+          const long long t0 = p.prof ? clock64() : 0;
           ptx::mbar_wait(empty + stage, phase ^ 1);
+          if (p.prof) tw += clock64() - t0;
           ptx::mbar_arrive_expect_tx(full + stage, kStageRows * kRowBytes);
           ptx::tma_load_4d(smem + stage * kStageBytes, &p.pmap, full + stage, 0, 0, 2 * r - 3, img);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.prof) { p.prof[blockIdx.x * 8 + 0] = clock64() - tstart; p.prof[blockIdx.x * 8 + 1] = tw; }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(128, kC);
-      const uint32_t w_a = ptx::smem_u32(smem + kOffW);
+      const uint64_t db0 = make_nosw_kmajor_desc(ptx::smem_u32(smem + kOffW), 1024, 128);
       int stage = 0;
       uint32_t phase = 0, it = 0;
+      long long t_acc = 0, t_full = 0;
+      const long long tstart = clock64();
       for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
         const int p0 = (band % p.bands_per_img) * PB;
         for (int r = max(2 * p0 - 1, 0); r <= 2 * (p0 + PB) - 1; ++r, ++it) {
           const int acc = it & 1;
+          const long long t0 = p.prof ? clock64() : 0;
           ptx::mbar_wait(tempty + acc, ((it >> 1) & 1) ^ 1);
+          const long long t1 = p.prof ? clock64() : 0;
           ptx::mbar_wait(full + stage, phase);
+          if (p.prof) { t_acc += t1 - t0; t_full += clock64() - t1; }
           ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(smem + stage * kStageBytes);
+          // descriptors differ only in their 16-byte-granular start address: one 64-bit add per operand
+          const uint64_t da0 = make_nosw_kmajor_desc(ptx::smem_u32(smem + stage * kStageBytes), 16, 128);
 #pragma unroll
           for (int t = 0; t < kMmas; ++t) {
             const int kh = t >> 1, jp = t & 1;
             // A row m = output column wo: pairs wo + 2*jp, wo + 2*jp + 1 of packed input row kh
-            const uint64_t da = make_nosw_kmajor_desc(a0 + kh * kRowBytes + jp * 32, 16, 128);
-            const uint64_t db = make_nosw_kmajor_desc(w_a + t * 2048, 1024, 128);
-            ptx::umma_f16(tmem_base + acc * kC, da, db, idesc, t != 0);
+            ptx::umma_f16(tmem_base + acc * kC, da0 + uint64_t((kh * kRowBytes + jp * 32) >> 4), db0 + uint64_t(t * (2048 >> 4)),
+                          idesc, t != 0);
           }
           ptx::umma_commit(empty + stage);
           ptx::umma_commit(tfull + acc);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.prof) { p.prof[blockIdx.x * 8 + 2] = clock64() - tstart; p.prof[blockIdx.x * 8 + 3] = t_acc; p.prof[blockIdx.x * 8 + 4] = t_full; p.prof[blockIdx.x * 8 + 5] = it; }
     }
   } else if (warp >= 4) {
     // ---- epilogue: thread = (conv output column wo = TMEM lane, half of the 64 channels) ----
+    // The 3x3/2 max-pool is separable.  Vertical: a thread sees every conv row of its own column, so it keeps
+    // the previous odd and even rows in registers (fp16, 16 + 16 registers) and, on every odd row, writes the
+    // column-wise maximum of the three rows to shared memory.  Horizontal: after one barrier per pooled row the
+    // 256 threads take the maximum of three neighbouring columns (stride 2) and emit the pooled row.
     const int e = warp - 4, q = e & 3, hf = e >> 2;           // q == warp % 4: the TMEM lane quarter
     const int wo = q * 32 + lane;
     const int et = threadIdx.x - 128;                         // 0..255
     const uint32_t hist_a = ptx::smem_u32(smem + kOffHist);
     const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + hf * 32;
-    // pooling role of this thread: channel chunk (8 channels) and pooled columns pw0 + 32 i
+    // horizontal role of this thread: channel chunk (8 channels) and pooled columns pw0 + 32 i
     const int chunk = et & 7, pw0 = et >> 3;
     float ps[8], pf[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ps[i] = p.pscale[chunk * 8 + i]; pf[i] = p.pshift[chunk * 8 + i]; }
-    uint32_t it = 0;
+    __half2 odd[16], even[16];                                // previous odd / even conv row of this column
+    float bias[32];                                           // this thread's 32 channels (constant for the kernel)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias[i] = s_bias[hf * 32 + i];
+    uint32_t it = 0, pooled = 0;
+    long long t_epi_wait = 0;
+    const long long t_epi_start = clock64();
     for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
       const int img = p.n_base + band / p.bands_per_img, p0 = (band % p.bands_per_img) * PB;
       for (int r = 2 * p0 - 1; r <= 2 * (p0 + PB) - 1; ++r) {
-        const uint32_t slot = hist_a + uint32_t((r + 3) % 3) * kHistBytes + uint32_t(wo) * 128u;
+        __half2 cur[16];
         if (r < 0) {
-          // zero padding row above the image takes part in the max (Q6)
+          // the zero padding row above the image takes part in the max (Q6)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)), "r"(0u) : "memory");
-          }
+          for (int k = 0; k < 16; ++k) cur[k] = __floats2half2_rn(0.f, 0.f);
         } else {
           const int acc = it & 1;
+          const long long t0 = p.prof ? clock64() : 0;
           ptx::mbar_wait(tfull + acc, (it >> 1) & 1);
+          if (p.prof) t_epi_wait += clock64() - t0;
           ptx::tc_fence_after();
           uint32_t v[32];
           __syncwarp();
@@ -192,72 +216,85 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
           __half *dbg = p.conv_dbg ? p.conv_dbg + ((size_t(img) * kConvW + r) * kConvW + wo) * kC + hf * 32 : nullptr;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float *b = s_bias + hf * 32 + 8 * j;
-            const float4 b0 = *reinterpret_cast<const float4 *>(b), b1 = *reinterpret_cast<const float4 *>(b + 4);
+            const float *b = bias + 8 * j;
             uint4 o;
-            o.x = pack2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
-            o.y = pack2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
-            o.z = pack2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
-            o.w = pack2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)),
-                         "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
-                         : "memory");
+            o.x = pack2(__uint_as_float(v[8 * j + 0]) + b[0], __uint_as_float(v[8 * j + 1]) + b[1]);
+            o.y = pack2(__uint_as_float(v[8 * j + 2]) + b[2], __uint_as_float(v[8 * j + 3]) + b[3]);
+            o.z = pack2(__uint_as_float(v[8 * j + 4]) + b[4], __uint_as_float(v[8 * j + 5]) + b[5]);
+            o.w = pack2(__uint_as_float(v[8 * j + 6]) + b[6], __uint_as_float(v[8 * j + 7]) + b[7]);
+            cur[4 * j + 0] = *reinterpret_cast<__half2 *>(&o.x); cur[4 * j + 1] = *reinterpret_cast<__half2 *>(&o.y);
+            cur[4 * j + 2] = *reinterpret_cast<__half2 *>(&o.z); cur[4 * j + 3] = *reinterpret_cast<__half2 *>(&o.w);
             if (dbg) reinterpret_cast<uint4 *>(dbg)[j] = o;
           }
         }
-        if ((r & 1) && r > 2 * p0 - 1) {
-          // rows r-2, r-1, r of THIS band are in the history (the band's first row 2*p0-1 is only a halo):
-          // pooled row pr = (r - 1) / 2
-          ptx::named_bar_sync(1, 256);
-          const int pr = (r - 1) >> 1;
-          const uint32_t s0 = hist_a + uint32_t((r + 1) % 3) * kHistBytes;   // (r - 2 + 3) % 3
-          const uint32_t s1 = hist_a + uint32_t((r + 2) % 3) * kHistBytes;
-          const uint32_t s2 = hist_a + uint32_t((r + 3) % 3) * kHistBytes;
+        if (!(r & 1)) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int pw = pw0 + 32 * i;
-            __half2 m[4];
+          for (int k = 0; k < 16; ++k) even[k] = cur[k];
+          continue;
+        }
+        if (r > 2 * p0 - 1) {
+          // rows r-2 (odd), r-1 (even), r of THIS band: vertical maximum of this column -> shared memory
+          const uint32_t slot = hist_a + (pooled & 1) * kHistBytes + uint32_t(wo) * 128u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) m[k] = __floats2half2_rn(0.f, 0.f);   // column -1 is zero padding; also the
-            bool first = pw > 0;                                                // identity when the window is full
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            __half2 *oh = reinterpret_cast<__half2 *>(&o);
 #pragma unroll
-            for (int dc = -1; dc <= 1; ++dc) {
-              const int col = 2 * pw + dc;
-              if (col < 0) continue;
-              const uint32_t off = uint32_t(col) * 128u + (uint32_t(chunk ^ (col & 7)) << 4);
-#pragma unroll
-              for (int rr = 0; rr < 3; ++rr) {
-                const uint4 x = ptx::lds_v4u((rr == 0 ? s0 : rr == 1 ? s1 : s2) + off);
-                const __half2 *xh = reinterpret_cast<const __half2 *>(&x);
-                if (first) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) m[k] = xh[k];
-                  first = false;
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], xh[k]);
-                }
-              }
-            }
-            const size_t o = ((size_t(img) * kPoolW + pr) * kPoolW + pw) * kC + chunk * 8;
-            uint4 ro;
-            __half2 *rh = reinterpret_cast<__half2 *>(&ro);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rh[k] = m[k];
-            if (p.raw) *reinterpret_cast<uint4 *>(p.raw + o) = ro;
-            uint4 po;
-            uint32_t *pw32 = reinterpret_cast<uint32_t *>(&po);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 y = __half22float2(m[k]);
-              pw32[k] = pack2_relu(fmaf(y.x, ps[2 * k], pf[2 * k]), fmaf(y.y, ps[2 * k + 1], pf[2 * k + 1]));
-            }
-            *reinterpret_cast<uint4 *>(p.pre + o) = po;
+            for (int k = 0; k < 4; ++k) oh[k] = __hmax2(__hmax2(odd[4 * j + k], even[4 * j + k]), cur[4 * j + k]);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)),
+                         "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                         : "memory");
           }
-          ptx::named_bar_sync(1, 256);             // the oldest history row may be overwritten now
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) odd[k] = cur[k];
+        if (r == 2 * p0 - 1) continue;                 // the band's first row is only a halo
+        // one barrier per pooled row: it also orders this row's reads before the write two rows later, which
+        // goes to the same slot (a thread arrives here only after its reads of the previous pooled row)
+        ptx::named_bar_sync(1, 256);
+        const int pr = (r - 1) >> 1;
+        const uint32_t vrow = hist_a + (pooled & 1) * kHistBytes;
+        ++pooled;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int pw = pw0 + 32 * i;
+          __half2 m[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = __floats2half2_rn(0.f, 0.f);     // column -1 is zero padding
+          bool first = pw > 0;
+#pragma unroll
+          for (int dc = -1; dc <= 1; ++dc) {
+            const int col = 2 * pw + dc;
+            if (col < 0) continue;
+            const uint4 x = ptx::lds_v4u(vrow + uint32_t(col) * 128u + (uint32_t(chunk ^ (col & 7)) << 4));
+            const __half2 *xh = reinterpret_cast<const __half2 *>(&x);
+            if (first) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) m[k] = xh[k];
+              first = false;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], xh[k]);
+            }
+          }
+          const size_t o = ((size_t(img) * kPoolW + pr) * kPoolW + pw) * kC + chunk * 8;
+          uint4 ro;
+          __half2 *rh = reinterpret_cast<__half2 *>(&ro);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rh[k] = m[k];
+          if (p.raw) *reinterpret_cast<uint4 *>(p.raw + o) = ro;
+          uint4 po;
+          uint32_t *pw32 = reinterpret_cast<uint32_t *>(&po);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 y = __half22float2(m[k]);
+            pw32[k] = pack2_relu(fmaf(y.x, ps[2 * k], pf[2 * k]), fmaf(y.y, ps[2 * k + 1], pf[2 * k + 1]));
+          }
+          *reinterpret_cast<uint4 *>(p.pre + o) = po;
         }
       }
     }
+    if (p.prof && e == 0 && lane == 0) { p.prof[blockIdx.x * 8 + 6] = clock64() - t_epi_start; p.prof[blockIdx.x * 8 + 7] = t_epi_wait; }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -331,9 +368,12 @@ metro_status root_make_image_map(void *map_out, const __half *packed, int n) {
       return fail(METRO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     fn = reinterpret_cast<EncodeTiledFn>(ptr);
   }
-  const cuuint64_t dims[4] = {8, cuuint64_t(kPairs), cuuint64_t(kSide), cuuint64_t(n)};
-  const cuuint64_t strides[3] = {16, cuuint64_t(kRowBytes), cuuint64_t(kRowBytes) * kSide};
-  const cuuint32_t box[4] = {8, cuuint32_t(kPairs), cuuint32_t(kStageRows), 1};
+  // a packed row (132 pairs x 8 fp16 = 2112 B) is described as 6 segments of 176 fp16: the TMA engine works
+  // through a box one innermost row at a time, and 16-byte innermost rows (one pair) made the copy of a
+  // 14.8 KB tile cost ~1800 cycles
+  const cuuint64_t dims[4] = {176, 6, cuuint64_t(kSide), cuuint64_t(n)};
+  const cuuint64_t strides[3] = {352, cuuint64_t(kRowBytes), cuuint64_t(kRowBytes) * kSide};
+  const cuuint32_t box[4] = {176, 6, cuuint32_t(kStageRows), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = fn(static_cast<CUtensorMap *>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(packed),
                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -354,7 +394,7 @@ metro_status img_pack_launch(const void *img, bool u8, __half *out, int n, cudaS
 
 metro_status root_fused_launch(const void *image_map, const __half *wpack, const float *bias, const float *pscale,
                                const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base,
-                               int num_sms, cudaStream_t stream) {
+                               int num_sms, cudaStream_t stream, long long *prof) {
   if (n == 0) return METRO_OK;
   static bool configured = false;
   if (!configured) {
@@ -365,6 +405,7 @@ metro_status root_fused_launch(const void *image_map, const __half *wpack, const
   p.pmap = *static_cast<const CUtensorMap *>(image_map);
   p.wpack = wpack; p.bias = bias; p.pscale = pscale; p.pshift = pshift;
   p.raw = raw; p.pre = pre; p.conv_dbg = conv_dbg;
+  p.prof = prof;
   p.n = n; p.n_base = n_base; p.pool_rows_per_band = 8; p.bands_per_img = kPoolW / 8;
   const int n_bands = n * p.bands_per_img;
   cudaLaunchConfig_t cfg = {};

@@ -10,7 +10,7 @@ using namespace metro;
 
 constexpr int kRing = 4, kCopyBytes = 16384;
 
-template <int N, int kPair, bool kCopy>
+template <int N, int kPair, bool kCopy, bool kNoSw = false>
 __global__ void __launch_bounds__(128, 1) k(long long *out, int iters, const unsigned char *src, size_t src_bytes) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar[2 + kRing];
@@ -39,7 +39,11 @@ __global__ void __launch_bounds__(128, 1) k(long long *out, int iters, const uns
   if (warp == 1 && lane == 0 && leader) {
     constexpr uint32_t idesc = ptx::make_idesc_f16(128 * kPair, N);
     const uint32_t sa = ptx::smem_u32(smem);
-    const uint64_t da = ptx::make_sw128_kmajor_desc(sa), db = ptx::make_sw128_kmajor_desc(sa + 16384);
+    uint64_t da = ptx::make_sw128_kmajor_desc(sa), db = ptx::make_sw128_kmajor_desc(sa + 16384);
+    if (kNoSw) {   // un-swizzled K-major operands: A rows 16 B apart with overlapping K chunks (LBO 16, SBO 128), B dense
+      da = uint64_t((sa >> 4) & 0x3FFF) | (uint64_t(16 >> 4) << 16) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
+      db = uint64_t(((sa + 16384) >> 4) & 0x3FFF) | (uint64_t(1024 >> 4) << 16) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
+    }
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -88,14 +92,14 @@ __global__ void __launch_bounds__(128, 1) k(long long *out, int iters, const uns
   }
 }
 
-template <int N, int kPair, bool kCopy>
+template <int N, int kPair, bool kCopy, bool kNoSw = false>
 void run(int grid, const unsigned char *src, size_t src_bytes) {
   long long *d, h[3] = {0, 0, 0};
   cudaMalloc(&d, 24);
   cudaMemset(d, 0, 24);
   const int iters = 2000;
   const int sm = 16384 + N * 128 + 2048 + kRing * kCopyBytes;
-  cudaFuncSetAttribute(k<N, kPair, kCopy>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(k<N, kPair, kCopy, kNoSw>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   for (int rep = 0; rep < 2; ++rep) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = sm;
@@ -103,11 +107,11 @@ void run(int grid, const unsigned char *src, size_t src_bytes) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kPair; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k<N, kPair, kCopy>, d, iters, src, src_bytes);
+    cudaLaunchKernelEx(&cfg, k<N, kPair, kCopy, kNoSw>, d, iters, src, src_bytes);
     cudaDeviceSynchronize();
   }
   cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
-  printf("N=%3d ctas/tile=%d copy=%d grid=%3d: %.1f cyc/MMA", N, kPair, int(kCopy), grid, double(h[0]) / (4.0 * iters));
+  printf("N=%3d ctas/tile=%d copy=%d noswizzle=%d grid=%3d: %.1f cyc/MMA", N, kPair, int(kCopy), int(kNoSw), grid, double(h[0]) / (4.0 * iters));
   if (kCopy) printf("   copy stream %.1f B/cyc/SM", double(h[1]) / double(h[2] ? h[2] : 1));
   printf("  (%s)\n", cudaGetErrorString(cudaGetLastError()));
   cudaFree(d);
@@ -118,7 +122,10 @@ int main() {
   const size_t src_bytes = size_t(64) << 20;      // 64 MB: L2 resident after the first pass
   cudaMalloc(&src, src_bytes + 65536 * 160);
   cudaMemset(src, 0, src_bytes + 65536 * 160);
-  for (int grid : {2, 148}) {
+  run<64, 1, false, true>(148, src, src_bytes);
+  run<128, 1, false, true>(148, src, src_bytes);
+  run<256, 1, false, true>(148, src, src_bytes);
+  for (int grid : {148}) {
     run<64, 1, false>(grid, src, src_bytes); run<64, 1, true>(grid, src, src_bytes);
     run<128, 1, false>(grid, src, src_bytes); run<128, 1, true>(grid, src, src_bytes);
     run<256, 1, false>(grid, src, src_bytes); run<256, 1, true>(grid, src, src_bytes);
