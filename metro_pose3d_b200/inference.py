@@ -57,6 +57,23 @@ class MetroModel:
                                          device, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def from_frozen_graph(cls, path_or_bytes, max_batch: int = 256, device: int = 0, head_dtype: str = 'f32',
+                          keep_activations: bool = False) -> 'MetroModel':
+        """Loads a model exported by the reference's ``main.export()`` (src/main.py:106-160): the binary GraphDef
+        is read without TensorFlow (``pb_import``), its constants become the weight blob, its ``output`` gather
+        indices the permutation and its ``joint_names`` / ``joint_edges`` constants the joint tables."""
+        from .joints import JointInfo
+        from .pb_import import import_frozen_graph, load_frozen_model
+        fm = import_frozen_graph(path_or_bytes) if isinstance(path_or_bytes, (bytes, bytearray)) \
+            else load_frozen_model(path_or_bytes)
+        model = cls(fm.arch, fm.stride, dataset='h36m', weights=fm.weights, max_batch=max_batch, device=device,
+                    head_dtype=head_dtype, keep_activations=keep_activations, n_joints_model=fm.n_joints_model,
+                    permutation=fm.permutation)
+        model.dataset = 'frozen-graph'
+        model.joint_info = JointInfo(fm.joint_names, [tuple(int(v) for v in e) for e in fm.joint_edges])
+        return model
+
     # -- the three fetches of the frozen graph ----------------------------------------------------
     @property
     def joint_names(self):
@@ -160,9 +177,19 @@ class MetroModel:
             pass
 
 
-def estimate_pose(images, model: MetroModel) -> Tuple[object, np.ndarray, list]:
+_loaded = {}
+
+
+def estimate_pose(images, model) -> Tuple[object, np.ndarray, list]:
     """Mirror of ``estimate_pose(images_tensor, model_path)`` (inference.py:31-43): returns
-    (poses [N,J,3] mm, joint_edges [E,2] int64, joint_names [J])."""
+    (poses [N,J,3] mm, joint_edges [E,2] int64, joint_names [J]).  ``model`` is a ``MetroModel`` or, as in the
+    reference, the path of an exported ``.pb`` file (loaded once per path)."""
+    if isinstance(model, (str, bytes)) and not isinstance(model, MetroModel):
+        key = model
+        if key not in _loaded:
+            n = int(images.shape[0])
+            _loaded[key] = MetroModel.from_frozen_graph(model, max_batch=max(n, 1))
+        model = _loaded[key]
     return model(images), model.joint_edges, model.joint_names
 
 

@@ -133,6 +133,27 @@ def test_in_kernel_preactivation_is_bit_identical():
     assert np.array_equal(a, b)
 
 
+def test_frozen_graph_import_runs_the_same_model(tmp_path):
+    """A frozen GraphDef written with the reference's node names (tests/pb_writer.py) and loaded through the
+    TensorFlow-free importer gives the poses of the model built from the same weights; estimate_pose accepts the
+    .pb path like the reference's inference.py:31-43."""
+    import sys, os, torch
+    sys.path.insert(0, os.path.dirname(__file__))
+    from pb_writer import frozen_graph
+    from metro_pose3d_b200.inference import MetroModel, estimate_pose
+    from metro_pose3d_b200.joints import exported_joint_info
+    spec = NetSpec('resnet_v2_50', 32, 17)
+    w = synth_weights(spec, 11)
+    ji = exported_joint_info('h36m')
+    path = tmp_path / 'model.pb'
+    path.write_bytes(frozen_graph(spec, w, export_permutation('h36m'), list(ji.names), np.asarray(ji.edges)))
+    img = torch.from_numpy(synth_images(3, seed=5)).cuda()
+    ref = MetroModel('resnet_v2_50', 32, 'h36m', weights=w, max_batch=3).infer(img).cpu().numpy()
+    poses, edges, names = estimate_pose(img, str(path))
+    assert np.array_equal(poses.cpu().numpy(), ref)
+    assert names == list(ji.names) and np.array_equal(edges, np.asarray(ji.edges))
+
+
 def test_uint8_ingestion_matches_float_path():
     import torch
     from metro_pose3d_b200.inference import MetroModel
