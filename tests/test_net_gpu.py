@@ -25,13 +25,14 @@ def _rel(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
 
 
-@pytest.mark.parametrize('arch,stride,ds', [('resnet_v2_50', 32, 'h36m'), ('resnet_v2_50', 16, 'h36m')])
-def test_layerwise_and_end_to_end(arch, stride, ds):
+@pytest.mark.parametrize('arch,stride,ds,n', [('resnet_v2_50', 32, 'h36m', 2), ('resnet_v2_50', 16, 'h36m', 2),
+                                             ('resnet_v2_101', 16, 'coco19', 1), ('resnet_v2_50', 8, 'coco19', 1)])
+def test_layerwise_and_end_to_end(arch, stride, ds, n):
     import torch
     from metro_pose3d_b200.inference import MetroModel, estimate_pose
-    n = 2
+    from metro_pose3d_b200.joints import model_joint_info
     perm = export_permutation(ds)
-    j = 17
+    j = model_joint_info(ds).n_joints
     spec = NetSpec(arch, stride, j)
     w = synth_weights(spec, 0)
     img = synth_images(n, seed=1000)
@@ -52,7 +53,9 @@ def test_layerwise_and_end_to_end(arch, stride, ds):
     got_head = model.debug_read('head').reshape(head.shape)
     report.append(('head', _rel(got_head, head)))
     worst = max(report, key=lambda r: r[1])
-    assert worst[1] < LAYER_REL, f'worst layer {worst}; first bad: {[r for r in report if r[1] >= LAYER_REL][:3]}'
+    # rounding flips random-walk with depth: 105 convolutions instead of 54 -> sqrt(2) wider band for ResNet-101
+    layer_rel = LAYER_REL * (1.5 if arch.endswith('101') else 1.0)
+    assert worst[1] < layer_rel, f'worst layer {worst}; first bad: {[r for r in report if r[1] >= layer_rel][:3]}'
     # strict: the decode of the path's own head tensor
     strict = np.abs(poses - ora.decode(got_head)).max()
     assert strict < DECODE_TOL_MM, f'decode on identical logits: max |err| = {strict:.3e} mm'
@@ -63,8 +66,9 @@ def test_layerwise_and_end_to_end(arch, stride, ds):
     err_half, err64 = np.abs(poses - ref).max(), np.abs(poses - p64).max()
     assert err_half < bound and err64 < bound, \
         f'end-to-end: |cuda-half| {err_half:.3f} mm, |cuda-fp64| {err64:.3f} mm, fp16 noise floor {noise:.3f} mm'
-    assert poses.shape == (n, 17, 3) and np.all(poses[:, 0] == 0)
-    assert edges.shape == (16, 2) and names[0] == 'pelv'
+    assert poses.shape == (n, len(perm), 3) and len(names) == len(perm)
+    if ds == 'h36m':
+        assert np.all(poses[:, 0] == 0) and edges.shape == (16, 2) and names[0] == 'pelv'
 
 
 def test_host_buffer_call_and_batch_invariance():
