@@ -192,6 +192,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
         const int cb2_0 = p.diag2 ? nt * (BLOCK_N / 64) : 0;
         const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
         left = k0 + n2;
+        if (p.tall) {
+          // 3x3 stride-1 convolution, "tall" staging: a stage holds, for one kernel column kw and one channel
+          // block, the (th + 2*rate) input rows that serve all three kernel rows (one column-shifted box; TMA
+          // zero fill pads left/right/top/bottom), plus the three weight boxes of that column.  A traffic per
+          // tile drops from 9 x th rows to 3 x (th + 2*rate) rows.
+          for (int kw = 0; kw < 3; ++kw)
+            for (int cb = 0; cb < p.cblk0; ++cb) {
+              if (prof) {
+                const long long t0 = clock64();
+                ptx::mbar_wait(empty + stage, phase ^ 1);
+                t_wait += clock64() - t0;
+              } else {
+                ptx::mbar_wait(empty + stage, phase ^ 1);
+              }
+              unsigned char *sa = tiles + stage * p.tall_stage_bytes;
+              const uint32_t fb = full0 + uint32_t(stage) * 8u;
+              if (is_a) {
+                if (rank == 0) ptx::mbar_arrive_expect_tx(full + stage, 2 * p.tall_stage_bytes);
+                ptx::tma_load_4d_pair(sa, &p.amap[1], fb, cb * kTileK, p.tap_dw[kw], h0 + p.tap_dh[0], n0);
+              } else {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+                  ptx::tma_load_2d_pair(sa + p.tall_a_bytes + kh * C::kBBytes, &p.bmap, fb,
+                                        ((kh * 3 + kw) * p.cblk0 + cb) * kTileK, ncol);
+              }
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+          continue;
+        }
         if (is_a) {
           for (int tap = 0; tap < p.taps; ++tap) {
             const CUtensorMap *am = &p.amap[p.tap_map[tap]];
@@ -239,6 +268,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
         }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
+        if (p.tall) {
+          const int n_st = 3 * p.cblk0;
+          for (int st = 0; st < n_st; ++st) {
+            {
+              const long long t0 = prof ? clock64() : 0;
+              ptx::mbar_wait(full + stage, phase);
+              if (prof) t_full += clock64() - t0;
+            }
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(tiles + stage * p.tall_stage_bytes);
+            const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
+            const uint64_t db = ptx::make_sw128_kmajor_desc(sa + p.tall_a_bytes);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              // kernel row kh reads the same box `rate` image rows further down (a multiple of 1 KB: the
+              // swizzle phase of the operand rows is unchanged)
+              const uint32_t offa = uint32_t(kh * p.tall_row_step) >> 4, offb = uint32_t(kh * C::kBBytes) >> 4;
+#pragma unroll
+              for (int k = 0; k < kTileK / 16; ++k)
+                ptx::umma_f16_pair(d_tmem, da + offa + 2 * k, db + offb + 2 * k, idesc, (st | kh | k) != 0);
+            }
+            ptx::umma_commit_pair(empty + stage, 3);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit_pair(tfull + acc, 3);
+          continue;
+        }
         for (int kb = 0; kb < n_kb; kb += C::kSub) {
           {
             const long long t0 = prof ? clock64() : 0;
@@ -632,7 +688,7 @@ metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks) {
   (void)k_blocks;
   ConvGemmParams &p = L.prm;
   const int k_sub = L.block_n <= 160 ? 2 : 1;      // Cfg::kSub
-  const int stage_bytes = k_sub * (kTileM * kTileK * 2 + (L.block_n / 2) * kTileK * 2);
+  const int stage_bytes = p.tall ? p.tall_stage_bytes : k_sub * (kTileM * kTileK * 2 + (L.block_n / 2) * kTileK * 2);
   const int n_out = L.direct ? 0 : (p.has_out1 ? 1 : 0) + (p.has_out2 ? 1 : 0);
   const int par_bytes = 2 * (p.has_out2 ? 3 : 2) * L.block_n * 4;     // two epilogue groups
   const int stage_out = kEpilogueWarps * n_out * kWarpStageBytes;

@@ -132,6 +132,20 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   if (g.stride == 1) {
     st = make_act_tensor_map(&p.amap[0], g.src, g.n_max, g.in_side, g.in_side, g.cin, 1, 0, 0, p.wo, p.th, p.nb);
     if (st != METRO_OK) return st;
+    // 3x3 SAME convolutions whose tile is whole rows of one crop: stage column-shifted tall boxes
+    static const bool no_tall = getenv("METRO_NO_TALL") != nullptr;
+    const int tall_rows = p.th + 2 * g.rate;
+    const int tall_bytes = tall_rows * p.wo * 128 + 3 * (L.block_n / 2) * 128;
+    if (!no_tall && g.k == 3 && p.nb == 1 && g.pad_lo == g.rate && !g.cin2 && !g.res && tall_rows <= 256 &&
+        L.block_n <= 128 && tall_bytes <= 72 * 1024) {   // narrow tiles are the ones bound by L2->SMEM traffic
+                                                         // (measured: no gain at 256 wide); >= 3 stages must fit
+      p.tall = 1;
+      p.tall_a_bytes = tall_rows * p.wo * 128;
+      p.tall_row_step = g.rate * p.wo * 128;
+      p.tall_stage_bytes = p.tall_a_bytes + 3 * (L.block_n / 2) * 128;
+      st = make_act_tensor_map(&p.amap[1], g.src, g.n_max, g.in_side, g.in_side, g.cin, 1, 0, 0, p.wo, tall_rows, 1);
+      if (st != METRO_OK) return st;
+    }
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
