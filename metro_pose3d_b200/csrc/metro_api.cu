@@ -759,18 +759,20 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
       }
       if (!ctas) continue;
       acc[2] *= 2; acc[3] *= 2; acc[7] *= 2; acc[13] *= 2; acc[14] *= 2;        // MMA-thread columns exist in the pair leaders only
-      if (l == 0) {   // fused root: producer total / wait-empty, MMA total / wait-acc / wait-full / rows, epilogue total / wait-acc
-        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (l == 0) {   // fused root kernel
+        double a[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         int ctas = 0;
         for (int c = 0; c < h->num_sms; ++c) {
-          const long long *r = &host[size_t(c) * 8];
+          const long long *r = &host[size_t(c) * 16];
           if (r[2] == 0) continue;
           ++ctas;
-          for (int k = 0; k < 8; ++k) a[k] += double(r[k]);
+          for (int k = 0; k < 16; ++k) a[k] += double(r[k]);
         }
         if (ctas)
-          fprintf(stderr, "root_fused (kcycles): prod total %.1f wait_empty %.1f | mma total %.1f wait_acc %.1f wait_full %.1f rows %.1f | epi total %.1f wait_acc %.1f\n",
-                  a[0] / ctas / 1e3, a[1] / ctas / 1e3, a[2] / ctas / 1e3, a[3] / ctas / 1e3, a[4] / ctas / 1e3, a[5] / ctas, a[6] / ctas / 1e3, a[7] / ctas / 1e3);
+          fprintf(stderr, "root_fused (kcycles): prod total %.1f wait_empty %.1f | mma total %.1f wait_acc %.1f wait_full %.1f rows %.1f | "
+                          "epi total %.1f wait_acc %.1f tmem_ld %.1f barrier %.1f pool %.1f\n",
+                  a[0] / ctas / 1e3, a[1] / ctas / 1e3, a[2] / ctas / 1e3, a[3] / ctas / 1e3, a[4] / ctas / 1e3, a[5] / ctas,
+                  a[6] / ctas / 1e3, a[7] / ctas / 1e3, a[8] / ctas / 1e3, a[9] / ctas / 1e3, a[10] / ctas / 1e3);
         continue;
       }
       const std::string &nm = h->gemms[l - 1].name;

@@ -51,7 +51,7 @@ struct alignas(64) RootParams {
   __half *raw, *pre;       // [n][64][64][64]; raw may be null
   __half *conv_dbg;        // optional [n][128][128][64]: conv1 output (keep_activations)
   int n, n_base, bands_per_img, pool_rows_per_band;   // crops n_base .. n_base + n of the buffers
-  long long *prof;         // optional [grid][8] role timers (cycles)
+  long long *prof;         // optional [grid][16] role timers (cycles)
 };
 
 constexpr int kOffW = kStages * kStageBytes;                 // 61440
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 8 + 0] = clock64() - tstart; p.prof[blockIdx.x * 8 + 1] = tw; }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = clock64() - tstart; p.prof[blockIdx.x * 16 + 1] = tw; }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 8 + 2] = clock64() - tstart; p.prof[blockIdx.x * 8 + 3] = t_acc; p.prof[blockIdx.x * 8 + 4] = t_full; p.prof[blockIdx.x * 8 + 5] = it; }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 2] = clock64() - tstart; p.prof[blockIdx.x * 16 + 3] = t_acc; p.prof[blockIdx.x * 16 + 4] = t_full; p.prof[blockIdx.x * 16 + 5] = it; }
     }
   } else if (warp >= 4) {
     // ---- epilogue: thread = (conv output column wo = TMEM lane, half of the 64 channels) ----
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
         }
       }
     }
-    if (p.prof && e == 0 && lane == 0) { p.prof[blockIdx.x * 8 + 6] = clock64() - t_epi_start; p.prof[blockIdx.x * 8 + 7] = t_epi_wait; }
+    if (p.prof && e == 0 && lane == 0) { p.prof[blockIdx.x * 16 + 6] = clock64() - t_epi_start; p.prof[blockIdx.x * 16 + 7] = t_epi_wait; }
   }
   ptx::tc_fence_before();
   __syncthreads();
