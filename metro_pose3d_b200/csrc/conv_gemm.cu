@@ -182,7 +182,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
         if (++sub == C::kSub || left == 0) { sub = 0; if (++stage == stages) { stage = 0; phase ^= 1; } }
       };
       for (int tile = pair; tile < n_tiles_total; tile += n_pairs) {
-        const int mp = tile / p.n_tiles, nt = tile - mp * p.n_tiles;
+        const int te = p.reverse ? n_tiles_total - 1 - tile : tile;   // work-list direction alternates between layers
+        const int mp = te / p.n_tiles, nt = te - mp * p.n_tiles;
         const int mt = 2 * mp + int(rank);          // this CTA's 128-pixel tile (may be one past the end: zero fill)
         int n0, h0;
         if (p.nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.th; }
@@ -258,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
       uint32_t phase = 0, it = 0;
       long long t_full = 0, t_acc = 0, t_mi = 0, t_mc = 0;
       for (int tile = pair; tile < n_tiles_total; tile += n_pairs, ++it) {
-        const int nt = tile % p.n_tiles;
+        const int nt = (p.reverse ? n_tiles_total - 1 - tile : tile) % p.n_tiles;
         const int n_kb = k0 + (p.diag2 ? min(BLOCK_N / 64, p.cblk1 - nt * (BLOCK_N / 64)) : p.cblk1);
         const int acc = it & 1;
         {
@@ -403,7 +404,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
     long long t_acc = 0, t_busy = 0, t_store = 0, t_ld = 0, t_math = 0, t_sts = 0, t_issue = 0, t_par = 0;
     uint32_t k = 0;
     for (int tile = pair + g * n_pairs; tile < n_tiles_total; tile += 2 * n_pairs, ++k) {
-      const int mp = tile / p.n_tiles, nt = tile - mp * p.n_tiles;
+      const int te = p.reverse ? n_tiles_total - 1 - tile : tile;
+      const int mp = te / p.n_tiles, nt = te - mp * p.n_tiles;
       const int m0 = p.m_base + (2 * mp + int(rank)) * kTileM + q * 32;
       const long long tp0 = prof ? clock64() : 0;
       if (nt != cur_nt) {                            // per-channel epilogue vectors of this N tile

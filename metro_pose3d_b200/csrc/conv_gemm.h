@@ -32,6 +32,8 @@ struct alignas(64) ConvGemmParams {
   // M tiling: a tile is 128 consecutive output pixels = th full rows of nb images
   int m_total, wo, ho, th, nb, tiles_per_img, m_tiles, n_tiles, cout;
   int n_base, m_base;    // first crop / first output row of the batch slice this launch works on
+  int reverse;           // walk the tile list backwards: consecutive layers alternate, so a layer starts on the
+                         // rows its producer wrote last (still resident in L2)
   // "tall" staging of 3x3 stride-1 convolutions: amap[1] is the (th + 2*rate)-row box, a stage = that box +
   // the three weight boxes of one kernel column; tall_row_step = rate * W * 128 bytes between kernel rows
   int tall, tall_a_bytes, tall_stage_bytes, tall_row_step;

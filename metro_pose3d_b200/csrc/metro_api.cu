@@ -218,6 +218,7 @@ struct metro_handle {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   float *stage_img = nullptr, *stage_pose = nullptr;
+  int alternate = 1;      // consecutive convolutions walk their tile lists in opposite directions (METRO_NO_ALTERNATE)
   int host_chunk = 64;    // crops per PCIe slice of metro_infer_host (METRO_HOST_CHUNK)
   int host_tail = 128;    // crops per slice of the deep blocks (METRO_HOST_TAIL; 0 = whole batch)
   int stem_gemms = 0;     // tensor-core convolutions that run per slice (up to the last 32x32-or-larger block)
@@ -380,6 +381,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     }
     cur_raw = nraw; cur_pre = npre;
   }
+  if (getenv("METRO_NO_ALTERNATE")) h.alternate = 0;
   if (const char *e = getenv("METRO_HOST_CHUNK")) h.host_chunk = atoi(e);
   if (const char *e = getenv("METRO_HOST_TAIL")) h.host_tail = atoi(e);
   // ---- logits (resnet_v2.py:234-236) -> head tensor ----
@@ -439,6 +441,7 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
   for (int li = 0; li < stem_gemms; ++li) {
     ConvGemmLaunch &L = h->gemms[li];
     conv_gemm_set_batch(L.prm, n, n_base);
+    L.prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;     // the root kernel walks forwards
     L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
@@ -458,6 +461,7 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
   for (size_t li = first_gemm; li < h->gemms.size(); ++li) {
     ConvGemmLaunch &L = h->gemms[li];
     conv_gemm_set_batch(L.prm, n, n_base);
+    L.prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;
     L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
