@@ -91,6 +91,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
     conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BLOCK_N>;
   constexpr int kParVecs = kMode == kDual ? 3 : 2;   // single/direct: scale, shift; dual: shift, scale2, shift2
+  constexpr bool kNarrowId = BLOCK_N == 256 && kMode != kDirect && !kXform;   // one K block per stage there
   // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B).  The kernel has no
   // static shared memory, so the dynamic window starts at the CTA's shared base; verified below.
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -163,6 +164,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
       // (with kXform every CTA has its own full barrier: its transform warps wait on it locally)
       const uint32_t full0 = ptx::mapa(ptx::smem_u32(full), kXform ? rank : 0);
       int sub = 0, left = 0;                        // K block within the stage; K blocks of the tile still to load
+      int id_blocks = 0;                            // identity K blocks at the end of the current tile
       auto acquire = [&]() -> unsigned char * {
         if (sub == 0) {
           if (prof) {
@@ -172,8 +174,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
           } else {
             ptx::mbar_wait(empty + stage, phase ^ 1);
           }
-          if (is_a && (kXform || rank == 0))
-            ptx::mbar_arrive_expect_tx(full + stage, (kXform ? 1 : 2) * C::kBlockBytes * min(C::kSub, left));
+          if (is_a && (kXform || rank == 0)) {
+            // identity-shortcut K blocks of a 256-wide tile carry a 64-channel slice of the identity only
+            // (narrow_id): 16 KB of activations + 32 weight rows per CTA
+            const bool narrow = kNarrowId && p.diag2 && left <= id_blocks;
+            ptx::mbar_arrive_expect_tx(full + stage, narrow ? 2 * (C::kABytes + 32 * kTileK * 2)
+                                                            : (kXform ? 1 : 2) * C::kBlockBytes * min(C::kSub, left));
+          }
         }
         return tiles + stage * C::kStageBytes + sub * C::kBlockBytes;
       };
@@ -193,6 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
         const int cb2_0 = p.diag2 ? nt * (BLOCK_N / 64) : 0;
         const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
         left = k0 + n2;
+        id_blocks = p.diag2 ? n2 : 0;
         if (p.tall) {
           // 3x3 stride-1 convolution, "tall" staging: a stage holds, for one kernel column kw and one channel
           // block, the (th + 2*rate) input rows that serve all three kernel rows (one column-shifted box; TMA
@@ -244,7 +252,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
           for (int kb = 0; kb < k0 + n2; ++kb) {
             const int kcol = (kb < k0 ? kb : kb + cb2_0) * kTileK;
             unsigned char *sa = acquire();
-            ptx::tma_load_2d_pair(sa + C::kABytes, &p.bmap, full0 + uint32_t(stage) * 8u, kcol, ncol);
+            if (kNarrowId && p.diag2 && kb >= k0)   // rows 64 j + 32 rank .. of this N tile: the 64x64 identity block, halved
+              ptx::tma_load_2d_pair(sa + C::kABytes, &p.bidmap, full0 + uint32_t(stage) * 8u, kcol,
+                                    nt * BLOCK_N + 64 * (kb - k0) + 32 * int(rank));
+            else
+              ptx::tma_load_2d_pair(sa + C::kABytes, &p.bmap, full0 + uint32_t(stage) * 8u, kcol, ncol);
             advance();
           }
         }
@@ -307,6 +319,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
           const uint32_t sa = ptx::smem_u32(tiles + stage * C::kStageBytes);
           const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
           const uint64_t db = ptx::make_sw128_kmajor_desc(sa + C::kABytes);
+          if (kNarrowId && p.diag2 && kb >= k0) {
+            // identity block j adds the shortcut's channels 64 j .. 64 j + 63: an N = 64 MMA on that column slice
+            constexpr uint32_t idesc64 = ptx::make_idesc_f16(2 * kTileM, 64);
+#pragma unroll
+            for (int k = 0; k < kTileK / 16; ++k)
+              ptx::umma_f16_pair(d_tmem + 64 * (kb - k0), da + 2 * k, db + 2 * k, idesc64, 1);
+          } else
 #pragma unroll
           for (int sb = 0; sb < C::kSub; ++sb) {
             if (sb > 0 && kb + sb >= n_kb) break;    // odd K-block count: the last stage is half full

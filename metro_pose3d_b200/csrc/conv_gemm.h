@@ -24,6 +24,7 @@ struct alignas(64) ConvGemmParams {
   CUtensorMap a2map;     // optional source 1 (1x1 on the output grid): the projection shortcut's input, or
                          // the identity shortcut's raw tensor (sub-sampled / shifted view) with diag2 = 1
   CUtensorMap bmap;      // packed weights [cout_pad][K_total] fp16, K-major
+  CUtensorMap bidmap;    // the same matrix with 32-row boxes: one CTA's half of a 64x64 identity block (diag2)
   CUtensorMap o1map;     // output 1  [M][cout] fp16 (TMA store), unused on the direct (fp32) path
   CUtensorMap o2map;     // output 2  [M][cout] fp16
   // K loop: taps x cblk0 blocks from source 0, then cblk1 blocks from source 1

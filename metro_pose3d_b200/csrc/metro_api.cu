@@ -128,6 +128,7 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   if (st != METRO_OK) return st;
   st = make_weight_tensor_map(&p.bmap, d_w, cout_pad, K, L.block_n);
   if (st != METRO_OK) return st;
+  if (g.res && (st = make_weight_tensor_map(&p.bidmap, d_w, cout_pad, K, 64)) != METRO_OK) return st;   // 32-row boxes
   // activations
   if (g.stride == 1) {
     st = make_act_tensor_map(&p.amap[0], g.src, g.n_max, g.in_side, g.in_side, g.cin, 1, 0, 0, p.wo, p.th, p.nb);
