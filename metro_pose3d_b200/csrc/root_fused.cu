@@ -41,6 +41,7 @@ constexpr int kStages = 4;
 constexpr int kMmas = 14;                            // 7 kernel rows x 2 K=16 steps
 constexpr int kWBytes = kMmas * 2048;                // [mma][k-chunk 2][cout-group 8][8 rows][16 B]
 constexpr int kHistBytes = kConvW * 128;             // one fp16 conv row: 128 px x 64 ch
+constexpr int kAccStages = 4;                        // TMEM accumulator ring: the epilogue drains rows in pairs
 constexpr int kThreads = 384;                        // 4 control warps + 8 epilogue warps (2 per TMEM lane quarter)
 
 struct alignas(64) RootParams {
@@ -58,7 +59,7 @@ constexpr int kOffW = kStages * kStageBytes;                 // 61440
 constexpr int kOffHist = kOffW + kWBytes;                    // 90112
 constexpr int kOffBias = kOffHist + 2 * kHistBytes;          // two slots of column-wise maxima
 constexpr int kOffBar = kOffBias + 256;
-constexpr int kSmemBytes = kOffBar + 128;
+constexpr int kSmemBytes = kOffBar + 256;
 
 // un-swizzled K-major operand: rows 16 B apart inside an 8-row core matrix, `sbo` between 8-row groups,
 // `lbo` between the two 8-element K chunks (cute/atom/mma_traits_sm100.hpp, LayoutType::INTERLEAVE)
@@ -85,8 +86,8 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
 __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_constant__ RootParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
-  uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = tfull + 2;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = tfull + kAccStages;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kAccStages);
   float *s_bias = reinterpret_cast<float *>(smem + kOffBias);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_bands = p.n * p.bands_per_img;
@@ -95,11 +96,11 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
   if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&p.pmap);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(full + i, 1); ptx::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 8); }
+    for (int i = 0; i < kAccStages; ++i) { ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 8); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(s_tmem, 128);
+    ptx::tmem_alloc(s_tmem, kAccStages * kC);
     ptx::tmem_relinquish();
   }
   // resident weights (already in operand layout) and the bias
@@ -145,9 +146,9 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
       for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
         const int p0 = (band % p.bands_per_img) * PB;
         for (int r = max(2 * p0 - 1, 0); r <= 2 * (p0 + PB) - 1; ++r, ++it) {
-          const int acc = it & 1;
+          const int acc = it % kAccStages;
           const long long t0 = p.prof ? clock64() : 0;
-          ptx::mbar_wait(tempty + acc, ((it >> 1) & 1) ^ 1);
+          ptx::mbar_wait(tempty + acc, ((it / kAccStages) & 1) ^ 1);
           const long long t1 = p.prof ? clock64() : 0;
           ptx::mbar_wait(full + stage, phase);
           if (p.prof) { t_acc += t1 - t0; t_full += clock64() - t1; }
@@ -184,75 +185,87 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
     float ps[8], pf[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ps[i] = p.pscale[chunk * 8 + i]; pf[i] = p.pshift[chunk * 8 + i]; }
-    __half2 odd[16], even[16];                                // previous odd / even conv row of this column
+    __half2 odd[16];                                          // previous odd conv row of this column
     float bias[32];                                           // this thread's 32 channels (constant for the kernel)
 #pragma unroll
     for (int i = 0; i < 32; ++i) bias[i] = s_bias[hf * 32 + i];
     uint32_t it = 0, pooled = 0;
     long long t_epi_wait = 0;
     const long long t_epi_start = clock64();
+    // TMEM row -> fp16 conv1 values (+ bias, the rounding point of the stored tensor) of this thread's 32 channels
+    auto to_half = [&](const uint32_t (&v)[32], __half2 (&h)[16], __half *dbg) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float *b = bias + 8 * j;
+        uint4 o;
+        o.x = pack2(__uint_as_float(v[8 * j + 0]) + b[0], __uint_as_float(v[8 * j + 1]) + b[1]);
+        o.y = pack2(__uint_as_float(v[8 * j + 2]) + b[2], __uint_as_float(v[8 * j + 3]) + b[3]);
+        o.z = pack2(__uint_as_float(v[8 * j + 4]) + b[4], __uint_as_float(v[8 * j + 5]) + b[5]);
+        o.w = pack2(__uint_as_float(v[8 * j + 6]) + b[6], __uint_as_float(v[8 * j + 7]) + b[7]);
+        h[4 * j + 0] = *reinterpret_cast<__half2 *>(&o.x); h[4 * j + 1] = *reinterpret_cast<__half2 *>(&o.y);
+        h[4 * j + 2] = *reinterpret_cast<__half2 *>(&o.z); h[4 * j + 3] = *reinterpret_cast<__half2 *>(&o.w);
+        if (dbg) reinterpret_cast<uint4 *>(dbg)[j] = o;
+      }
+    };
+    auto wait_row = [&](uint32_t i) {
+      const long long t0 = p.prof ? clock64() : 0;
+      ptx::mbar_wait(tfull + i % kAccStages, (i / kAccStages) & 1);
+      if (p.prof) t_epi_wait += clock64() - t0;
+    };
     for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
       const int img = p.n_base + band / p.bands_per_img, p0 = (band % p.bands_per_img) * PB;
-      for (int r = 2 * p0 - 1; r <= 2 * (p0 + PB) - 1; ++r) {
-        __half2 cur[16];
-        if (r < 0) {
-          // the zero padding row above the image takes part in the max (Q6)
+      __half *dbg0 = p.conv_dbg ? p.conv_dbg + (size_t(img) * kConvW * kConvW + wo) * kC + hf * 32 : nullptr;
+      // halo row 2*p0 - 1 (the zero padding row above the image takes part in the max, Q6)
+      if (p0 == 0) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) cur[k] = __floats2half2_rn(0.f, 0.f);
-        } else {
-          const int acc = it & 1;
-          const long long t0 = p.prof ? clock64() : 0;
-          ptx::mbar_wait(tfull + acc, (it >> 1) & 1);
-          if (p.prof) t_epi_wait += clock64() - t0;
-          ptx::tc_fence_after();
-          uint32_t v[32];
-          __syncwarp();
-          ptx::tmem_ld_32x32(taddr0 + acc * kC, v);
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty + acc);
-          ++it;
-          __half *dbg = p.conv_dbg ? p.conv_dbg + ((size_t(img) * kConvW + r) * kConvW + wo) * kC + hf * 32 : nullptr;
+        for (int k = 0; k < 16; ++k) odd[k] = __floats2half2_rn(0.f, 0.f);
+      } else {
+        wait_row(it);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(taddr0 + (it % kAccStages) * kC, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty + it % kAccStages);
+        ++it;
+        to_half(v, odd, dbg0 ? dbg0 + size_t(2 * p0 - 1) * kConvW * kC : nullptr);
+      }
+      for (int pr = p0; pr < p0 + PB; ++pr) {
+        // conv rows 2*pr (even) and 2*pr + 1 (odd) together: one wake-up, two TMEM loads in flight
+        wait_row(it);
+        wait_row(it + 1);
+        ptx::tc_fence_after();
+        uint32_t va[32], vb[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(taddr0 + (it % kAccStages) * kC, va);
+        ptx::tmem_ld_32x32(taddr0 + ((it + 1) % kAccStages) * kC, vb);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { ptx::mbar_arrive(tempty + it % kAccStages); ptx::mbar_arrive(tempty + (it + 1) % kAccStages); }
+        it += 2;
+        __half2 ev[16], cur[16];
+        to_half(va, ev, dbg0 ? dbg0 + size_t(2 * pr) * kConvW * kC : nullptr);
+        to_half(vb, cur, dbg0 ? dbg0 + size_t(2 * pr + 1) * kConvW * kC : nullptr);
+        // vertical maximum of rows 2*pr - 1, 2*pr, 2*pr + 1 of this column -> shared memory
+        const uint32_t slot = hist_a + (pooled & 1) * kHistBytes + uint32_t(wo) * 128u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float *b = bias + 8 * j;
-            uint4 o;
-            o.x = pack2(__uint_as_float(v[8 * j + 0]) + b[0], __uint_as_float(v[8 * j + 1]) + b[1]);
-            o.y = pack2(__uint_as_float(v[8 * j + 2]) + b[2], __uint_as_float(v[8 * j + 3]) + b[3]);
-            o.z = pack2(__uint_as_float(v[8 * j + 4]) + b[4], __uint_as_float(v[8 * j + 5]) + b[5]);
-            o.w = pack2(__uint_as_float(v[8 * j + 6]) + b[6], __uint_as_float(v[8 * j + 7]) + b[7]);
-            cur[4 * j + 0] = *reinterpret_cast<__half2 *>(&o.x); cur[4 * j + 1] = *reinterpret_cast<__half2 *>(&o.y);
-            cur[4 * j + 2] = *reinterpret_cast<__half2 *>(&o.z); cur[4 * j + 3] = *reinterpret_cast<__half2 *>(&o.w);
-            if (dbg) reinterpret_cast<uint4 *>(dbg)[j] = o;
-          }
-        }
-        if (!(r & 1)) {
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) even[k] = cur[k];
-          continue;
-        }
-        if (r > 2 * p0 - 1) {
-          // rows r-2 (odd), r-1 (even), r of THIS band: vertical maximum of this column -> shared memory
-          const uint32_t slot = hist_a + (pooled & 1) * kHistBytes + uint32_t(wo) * 128u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            __half2 *oh = reinterpret_cast<__half2 *>(&o);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) oh[k] = __hmax2(__hmax2(odd[4 * j + k], even[4 * j + k]), cur[4 * j + k]);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)),
-                         "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
-                         : "memory");
-          }
+          for (int k = 0; k < 4; ++k) oh[k] = __hmax2(__hmax2(odd[4 * j + k], ev[4 * j + k]), cur[4 * j + k]);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)),
+                       "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                       : "memory");
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) odd[k] = cur[k];
-        if (r == 2 * p0 - 1) continue;                 // the band's first row is only a halo
         // one barrier per pooled row: it also orders this row's reads before the write two rows later, which
         // goes to the same slot (a thread arrives here only after its reads of the previous pooled row)
         ptx::named_bar_sync(1, 256);
-        const int pr = (r - 1) >> 1;
         const uint32_t vrow = hist_a + (pooled & 1) * kHistBytes;
         ++pooled;
 #pragma unroll
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 128);
+    ptx::tmem_dealloc(tmem_base, kAccStages * kC);
   }
 }
 
