@@ -3,23 +3,29 @@
 //   D[M = N*Ho*Wo pixels, Cout] = sum over taps (kh,kw) and 64-channel blocks of
 //                                 X[n, ho*s + kh*r - pad, wo*s + kw*r - pad, c] * W[kh,kw,c,cout]
 //
-// One kernel serves every convolution of the ResNet body (resnet_v2.py:123-136,234-236):
+// One kernel template serves every convolution of the residual body and the logits head
+// (resnet_v2.py:123-136,234-236); DESIGN.md section 3.1 has the measured rationale of each choice:
+//   * tile = CTA pair (cluster of 2, tcgen05 cta_group::2): 256 output pixels x BLOCK_N channels; each CTA
+//     stages its own 128 pixel rows of A and half of the weight rows, the leader issues M = 256 MMAs.
 //   * A operand: NHWC fp16 activations fetched by TMA as 4-D boxes [64 ch, Wo, th, nb] (128 output
 //     pixels = th full output rows of nb crops) at the tap's shifted coordinate; TMA's out-of-bounds
 //     zero fill IS the convolution's zero padding (resnet_utils.py:120-135), dilation is a larger
 //     shift, and a stride-2 conv reads four (row,col)-parity views of the input (tensor maps with
-//     doubled strides), so no im2col buffer and no strided gather exists anywhere.
-//   * B operand: weights pre-packed [Cout][K] fp16 K-major, 2-D TMA boxes [64, BLOCK_N].
+//     doubled strides), so no im2col buffer and no strided gather exists anywhere.  Narrow 3x3 stride-1
+//     convolutions stage one tall column-shifted box per kernel column that serves all three kernel rows.
+//   * B operand: weights pre-packed [Cout][K] fp16 K-major, 2-D TMA boxes [64, BLOCK_N / 2].
 //   * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
 //   * accumulators live in TMEM (fp32), double-buffered so the epilogue of tile i overlaps the
-//     main loop of tile i+1; the kernel is persistent (one CTA per SM, static round-robin tiles).
-//   * warp roles: 0 = TMA producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator,
-//     4..7 = epilogue (thread = accumulator row = output pixel).
-//   * epilogue fuses folded BN / bias, the residual add (identity shortcut, optionally sub-sampled
-//     with the centred-stride offset, resnet_v2.py:120-121), ReLU, and the *next* layer's
-//     pre-activation BN+ReLU as a second output (resnet_v2.py:119), so no stand-alone
-//     normalisation pass ever touches HBM.  The projection shortcut (resnet_v2.py:123-125) is a
-//     second A source accumulated into the same TMEM tile (K concatenation).
+//     main loop of tile i+1; the kernel is persistent (one CTA per SM, static round-robin pair tiles,
+//     walked forwards or backwards on alternating layers).
+//   * warp roles: 0 = TMA producer (A), 3 = TMA producer (B), 1 = MMA issuer (one elected thread),
+//     2 = TMEM allocator, 4..11 = epilogue in two groups (group g drains accumulator stage g; thread =
+//     accumulator row = output pixel), 12..15 (kXform only) = A-tile pre-activation.
+//   * epilogue fuses folded BN / bias, ReLU and the *next* layer's pre-activation BN+ReLU as a second
+//     output (resnet_v2.py:119), so no stand-alone normalisation pass ever touches HBM.  Both kinds of
+//     shortcut are extra K blocks of the same accumulator: the projection shortcut (resnet_v2.py:123-125)
+//     against its 1x1 filters, the identity shortcut (optionally sub-sampled with the centred-stride
+//     offset, resnet_v2.py:120-121) against identity weights.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
