@@ -26,7 +26,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize('arch,stride,ds,n', [('resnet_v2_50', 32, 'h36m', 2), ('resnet_v2_50', 16, 'h36m', 2),
-                                             ('resnet_v2_101', 16, 'coco19', 1), ('resnet_v2_50', 8, 'coco19', 1)])
+                                             ('resnet_v2_101', 16, 'coco19', 1), ('resnet_v2_50', 8, 'coco19', 1),
+                                             ('resnet_v2_50', 4, 'coco19', 1)])
 def test_layerwise_and_end_to_end(arch, stride, ds, n):
     import torch
     from metro_pose3d_b200.inference import MetroModel, estimate_pose
