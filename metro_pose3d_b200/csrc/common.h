@@ -32,7 +32,7 @@ struct SoftargmaxLaunch {
   int n_out, root;
   int perm[kMaxJointsOut];
   double mul_x, mul_y, mul_z;  // mm per unit of (Sx/S), (Sy/S), (Sz/S)
-  int splits, lanes, slots, ppc, rpt, tiles, max_ctas, off_hw, off_ch, vec;
+  int splits, lanes, slots, ppc, rpt, tiles, max_ctas, off_hw, off_ch, vec, stages;
   int head_f16;
 };
 metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLaunch &L);

@@ -34,6 +34,8 @@
 // per-split records; the workspace counters are left zeroed for the next launch.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -42,7 +44,7 @@ namespace metro {
 namespace {
 
 constexpr int kMaxThreads = 512;
-constexpr int kStages = 2;
+constexpr int kMaxStages = 4;        // shared-memory ring depth is a plan parameter (L.stages <= kMaxStages)
 constexpr int kGroup = 8;            // pixel steps per fp32 partial sum (first level)
 constexpr int kMaxSteps = 32;        // pixel steps per thread per tile
 constexpr float kLog2e = 1.4426950408889634f;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 192 ? 3 : 1) softargmax_kernel(c
   cons.open(blockIdx.x, n_items, p.splits, p.tiles);
   prod = cons;
   if (tid == 0) {
-    for (int st = 0; st < kStages; ++st) ptx::mbar_init(full + st, 1);
+    for (int st = 0; st < p.stages; ++st) ptx::mbar_init(full + st, 1);
     ptx::fence_mbar_init();
   }
   for (int q = tid; q < p.ppc; q += nthreads) {
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 192 ? 3 : 1) softargmax_kernel(c
   ptx::griddep_wait();
   ptx::griddep_launch_dependents();
   if (tid == 0) {
-    for (int st = 0; st < kStages && !prod.done(n_items); ++st) { issue(prod, st); advance(prod); }
+    for (int st = 0; st < p.stages && !prod.done(n_items); ++st) { issue(prod, st); advance(prod); }
   }
   __syncthreads();                       // barriers initialised and the (row, column) table written
 
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 192 ? 3 : 1) softargmax_kernel(c
     }
     __syncthreads();                     // every thread is done with this ring stage
     if (tid == 0 && !prod.done(n_items)) { issue(prod, stage); advance(prod); }
-    if (++stage == kStages) { stage = 0; phase ^= 1; }
+    if (++stage == p.stages) { stage = 0; phase ^= 1; }
     const int item = cons.item;
     const bool item_done = (cons.t + 1 >= cons.t1);
     advance(cons);
@@ -362,7 +364,7 @@ size_t tile_bytes(const SoftargmaxLaunch &L) {
 size_t hw_bytes(const SoftargmaxLaunch &L) { return (size_t(L.ppc) * 8 + 127) & ~size_t(127); }
 
 size_t smem_bytes(const SoftargmaxLaunch &L) {
-  return kStages * tile_bytes(L) + hw_bytes(L) + size_t(L.C) * sizeof(ChanRec) + size_t(3) * L.J * 8 + kStages * 8 + 16;
+  return L.stages * tile_bytes(L) + hw_bytes(L) + size_t(L.C) * sizeof(ChanRec) + size_t(3) * L.J * 8 + kMaxStages * 8 + 16;
 }
 
 template <int VEC, int LANES, bool F16, int MAXT>
@@ -433,7 +435,14 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   const int row_bytes = L.C * (L.head_f16 ? 2 : 4);
   // tile: ~36 KB of whole rows, or an even part of one row when a row is larger than that (measured on
   // B200: larger tiles amortise the per-tile bookkeeping better than more resident CTAs hide latency)
-  const int budget_px = (40 * 1024) / row_bytes;
+  // ring: `stages` tiles of ~`tile_kb` KB in flight per CTA (tunable for experiments: METRO_SAM_STAGES / METRO_SAM_TILE_KB)
+  int tile_kb = 40;
+  L.stages = 2;
+  if (const char *e = getenv("METRO_SAM_STAGES")) L.stages = atoi(e);
+  if (const char *e = getenv("METRO_SAM_TILE_KB")) tile_kb = atoi(e);
+  if (L.stages < 2) L.stages = 2;
+  if (L.stages > kMaxStages) L.stages = kMaxStages;
+  const int budget_px = (tile_kb * 1024) / row_bytes;
   int ppc;
   if (budget_px >= L.W) {
     int rows = budget_px / L.W;
@@ -460,7 +469,7 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   L.splits = splits;
   L.max_ctas = 148 * 3;
   L.rpt = L.ppc / lanes;
-  L.off_hw = int(kStages * tile_bytes(L));
+  L.off_hw = int(L.stages * tile_bytes(L));
   L.off_ch = L.off_hw + int(hw_bytes(L));
   if (smem_bytes(L) > 200 * 1024) return fail(METRO_ERR_VALUE, "softargmax: shared memory budget exceeded");
   return METRO_OK;
