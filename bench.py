@@ -349,9 +349,10 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16 operands / f32 accumulate', 'data': 'synthetic',
+        'dtype': 'f16', 'data': 'synthetic',
         'config': {'workload': f'config {args.config}: {arch} stride_{stride} {j} joints, batch {n}/GPU',
                    'global_batch': n * world, 'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (2 rotating batches)',
+                   'arithmetic': 'f16 operands (the reference default, src/options.py:73), f32 accumulate, f32 head and decode',
                    'head_dtype': args.head_dtype, 'gflop_per_crop': spec.flops_per_crop / 1e9,
                    'tensor_frac_whole_step': spec.flops_per_crop * n / (ms * 1e-3) / 1e12 / tf_sust},
         'e2e': e2e, 'gpu_launches': model.launch_count(n) * args.steps,
