@@ -32,7 +32,10 @@ struct SoftargmaxLaunch {
   int n_out, root;
   int perm[kMaxJointsOut];
   double mul_x, mul_y, mul_z;  // mm per unit of (Sx/S), (Sy/S), (Sz/S)
-  int splits, lanes, slots, ppc, rpt, tiles, max_ctas, off_hw, off_ch, vec, stages;
+  int splits, ipx;         // work items per crop and pixels per item (shape-only rule)
+  int lanes, slots, vec;   // CTA = slots channel words x lanes pixel lanes; vec channels per word
+  int tpj;                 // threads per joint in the merge (power of two <= 32)
+  long long *prof;         // debug (METRO_SAM_PROF): 8 clock64 stamps per CTA, or null
   int head_f16;
 };
 metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLaunch &L);

@@ -5,6 +5,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.h"
@@ -616,23 +617,51 @@ metro_status metro_infer_host(metro_handle *h, const float *images_host, int32_t
   int tail = h->host_tail > 0 ? (h->host_tail + chunk - 1) / chunk * chunk : n;
   if (chunk == n) tail = n;
   int i = 0, tail_lo = 0;
+  // METRO_HOST_TRACE=1: timestamps of every slice's copy / stem / tail, printed after the call (debug only)
+  static const bool trace = std::getenv("METRO_HOST_TRACE") != nullptr;
+  std::vector<std::pair<const char *, cudaEvent_t>> marks;
+  auto mark = [&](const char *what, cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    marks.emplace_back(what, e);
+  };
+  if (trace) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_stream); }
+  mark("start", h->copy_stream);
   for (int lo = 0; lo < n; lo += chunk, ++i) {
     const int cnt = lo + chunk <= n ? chunk : n - lo;
     METRO_CUDA(cudaMemcpyAsync(h->stage_img + size_t(lo) * img_elems, images_host + size_t(lo) * img_elems, img_bytes * cnt,
                                cudaMemcpyHostToDevice, h->copy_stream));
     METRO_CUDA(cudaEventRecord(h->ev_copied[i & 1], h->copy_stream));
+    mark("h2d", h->copy_stream);
     METRO_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied[i & 1], 0));
     metro_status st = run_stem(h, h->stage_img + size_t(lo) * img_elems, false, cnt, lo, stem_gemms, h->stream, nullptr);
     if (st != METRO_OK) return st;
+    mark("stem", h->stream);
     const int done = lo + cnt;
-    if (done - tail_lo >= tail || done == n) {
+    // once no more than one tail slice is left to arrive, the deep blocks follow every stem slice, so that only
+    // one stem slice and one 64-crop tail remain after the last byte has crossed PCIe
+    if (done - tail_lo >= tail || n - tail_lo <= tail || done == n) {
       st = run_tail(h, done - tail_lo, tail_lo, stem_gemms, h->stage_pose, h->stream, nullptr);
       if (st != METRO_OK) return st;
       tail_lo = done;
+      mark("tail", h->stream);
     }
   }
   METRO_CUDA(cudaMemcpyAsync(poses_host, h->stage_pose, pose_bytes * n, cudaMemcpyDeviceToHost, h->stream));
+  mark("d2h", h->stream);
   METRO_CUDA(cudaStreamSynchronize(h->stream));
+  if (trace) {
+    std::fprintf(stderr, "[metro host trace]");
+    for (auto &m : marks) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[0].second, m.second);
+      std::fprintf(stderr, " %s=%.3f", m.first, ms);
+    }
+    std::fprintf(stderr, "\n");
+    for (auto &m : marks) cudaEventDestroy(m.second);
+  }
   return METRO_OK;
 }
 

@@ -8,33 +8,36 @@
 //   tfu3d.py:23-25         root_relative (last model joint)
 //   main.py:127            gather(permutation)
 // which materialise [N,J,H,W,D] and re-read it about ten times.  Here the NHWC head [N,H,W,D*J]
-// (channel c = d*J + j) is read exactly once with 16-byte coalesced loads and
+// (channel c = d*J + j) is read exactly once with 16-byte coalesced streaming loads and
 //   out[n,jo,:] = (E_j[w]/(W-1), E_j[h]/(H-1), E_j[d]/(D-1)) - same for the root, times mm scales.
 //
-// Layout of work: the head tensor of one crop is a contiguous byte range; it is cut into tiles of
-// whole heatmap rows (~35 KB).  A CTA is PERSISTENT over work items (item = one crop, or one of
-// `splits` row ranges of a large crop) and streams each item tile by tile through a 2-stage shared
-// memory ring: an elected thread issues bulk asynchronous copies (cp.async.bulk, the TMA engine) one
-// ring ahead -- also across item boundaries -- so the HBM stream never waits for arithmetic, and with
-// 2-3 CTAs per SM ~150 KB per SM are in flight without costing a register.
-// thread = (16-byte channel slot, pixel lane); a thread walks pixels lane, lane+LANES, ... of a tile,
-// so shared-memory reads are conflict-free 16-byte words, and it keeps its channels' running sums in
-// registers for the whole item: the only cross-thread work (lane shuffle, depth merge, output) happens
-// once per item, not per tile.  The kernel is close to instruction bound at HBM speed (one exp per
-// element), so the inner loop is 2-wide packed fp32 (FFMA2/FADD2) and carries no address arithmetic.
+// Layout of work: the head tensor of a crop is a contiguous run of 16-byte words (8-byte words for an fp16
+// head), `slots` words per pixel.  A work item is one crop or -- for heatmaps above 256 pixels -- one of up to
+// four row-major pixel ranges (a rule that depends on the heatmap shape only), one CTA per item, two CTAs
+// resident per SM.  The CTA has slots x lanes threads (272-304 for the reference shapes); thread t owns channel
+// slot t % slots and walks pixels (t / slots), + lanes, ...: consecutive threads read consecutive words, so
+// every warp request is 512 contiguous bytes.  The stream goes global -> registers in chunks of 8 words per
+// thread; a register word is reloaded with the next chunk's data after its last use, so the loads of chunk
+// k+1 are in flight underneath the arithmetic of chunk k.  No shared-memory staging, no block-wide
+// synchronisation inside the stream, ~18 warps per SM to hide the latency of the one exp per element.
+// (The previous design staged tiles through a cp.async.bulk ring with 5-warp CTAs; it moved bytes as fast
+// but its two shared-memory passes per tile and serial per-item merge cost 3-4 us per launch.)
+// The per-thread records (4 channels) meet in shared memory once per item, where 16 threads per joint merge
+// the lanes x depth records with one butterfly.  A CTA's life outside the stream is ~2500 cycles (records,
+// merge, output), which is why items are long and few.
 //
 // Numerics: exp(x - max) is evaluated in base 2 against an INTEGER exponent k >= max * log2(e) kept
 // per (thread, channel) and raised -- with an exact power-of-two re-scale of the running sums -- when a
-// later tile holds a larger value.  Per-tile partial sums (<= 32 terms, two-level) are fp32; running
-// sums and every merge (tiles -> lanes -> depth -> joint -> CTA splits) are fp64 re-scaled by exact
-// powers of two: no transcendental and no rounding in any merge weight.  The only fp32 roundings are
-// ex2.approx per element and the short per-tile sums, which keeps the result within 1e-3 mm of the
-// float64 oracle.
-// When a crop is split over several CTAs the last CTA to finish (ticket counter) merges the
-// per-split records; the workspace counters are left zeroed for the next launch.
+// later chunk holds a larger value.  Per-thread sums are fp32, two-level (8 terms, then chunks); every
+// merge (lanes x depth -> joint -> CTA splits) is fp64 with weights that are exact powers of two applied
+// in fp32 (an exact scaling): no transcendental and no rounding in any merge weight.  The only fp32 roundings are ex2.approx per
+// element and the short per-thread sums, which keeps the result within 1e-3 mm of the float64 oracle.
+// When a crop is split over several CTAs the last CTA to finish (ticket counter) merges the per-split
+// records; the workspace counters are left zeroed for the next launch.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -43,347 +46,390 @@ namespace metro {
 
 namespace {
 
-constexpr int kMaxThreads = 512;
-constexpr int kMaxStages = 4;        // shared-memory ring depth is a plan parameter (L.stages <= kMaxStages)
-constexpr int kGroup = 8;            // pixel steps per fp32 partial sum (first level)
-constexpr int kMaxSteps = 32;        // pixel steps per thread per tile
+constexpr int kMaxThreads = 640;
+constexpr int kItemPixels = 256;     // default pixels per work item
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNone = -3.0e38f;   // exponent of an empty record
 
-// VEC channels of one pixel from a 32-bit shared-memory address, as VEC/2 float pairs
-template <int VEC, bool F16>
-struct Vec;
-template <>
-struct Vec<4, false> {  // 4 x fp32, 16 bytes
-  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[2]) {
-    const float4 v = ptx::lds_v4(addr);
-    x[0] = make_float2(v.x, v.y); x[1] = make_float2(v.z, v.w);
-  }
+// one global word of VEC channels = RAW 32-bit registers
+template <int RAW>
+struct Raw {
+  uint32_t r[RAW];
 };
-template <>
-struct Vec<2, false> {  // 2 x fp32, 8 bytes
-  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[1]) { x[0] = ptx::lds_v2(addr); }
-};
-template <>
-struct Vec<8, true> {  // 8 x fp16, 16 bytes
-  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[4]) {
-    const uint4 r = ptx::lds_v4u(addr);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+// predicated streaming load: the word, or `fill` in every register when `on` is zero (no branch, so that the
+// compiler keeps the load where it is written -- in the middle of the previous chunk's arithmetic)
+__device__ __forceinline__ void ldg_stream(Raw<4> &v, const void *p, int on, uint32_t fill) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.b32 %0, %6;\n\tmov.b32 %1, %6;\n\tmov.b32 %2, %6;\n\tmov.b32 %3, %6;\n\t"
+      "@q ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}\n"
+      : "=&r"(v.r[0]), "=&r"(v.r[1]), "=&r"(v.r[2]), "=&r"(v.r[3])
+      : "l"(p), "r"(on), "r"(fill));
+}
+__device__ __forceinline__ void ldg_stream(Raw<2> &v, const void *p, int on, uint32_t fill) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "mov.b32 %0, %4;\n\tmov.b32 %1, %4;\n\t"
+      "@q ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];\n\t}\n"
+      : "=&r"(v.r[0]), "=&r"(v.r[1])
+      : "l"(p), "r"(on), "r"(fill));
+}
+// RAW registers -> V2 float pairs
+template <int RAW, bool F16, int V2>
+__device__ __forceinline__ void unpack(const Raw<RAW> &v, float2 (&x)[V2]) {
+  if constexpr (F16) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
-  }
-};
-template <>
-struct Vec<4, true> {  // 4 x fp16, 8 bytes
-  static __device__ __forceinline__ void load(uint32_t addr, float2 (&x)[2]) {
-    const float2 r = ptx::lds_v2(addr);
-    const uint32_t w[2] = {__float_as_uint(r.x), __float_as_uint(r.y)};
+    for (int i = 0; i < V2; ++i) x[i] = __half22float2(*reinterpret_cast<const __half2 *>(&v.r[i]));
+  } else {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) x[i] = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+    for (int i = 0; i < V2; ++i) x[i] = make_float2(__uint_as_float(v.r[2 * i]), __uint_as_float(v.r[2 * i + 1]));
   }
-};
+}
 
 // 2^d for an integer-valued d <= 0 (exact; flushes to zero far below the range that can matter).
 __device__ __forceinline__ double pow2_neg(float d) {
   const int e = int(fmaxf(d, -1000.f));
   return __longlong_as_double((long long)(1023 + e) << 52);
 }
+__device__ __forceinline__ float pow2_neg_f32(float d) {   // same in fp32, d clamped to the normal range
+  const int e = int(fmaxf(d, -126.f));
+  return __int_as_float((127 + e) << 23);
+}
+// 1/a for a sum of exponentials (0.5 <= a < 2^30: well inside fp32 range): fp32 seed, two Newton steps in
+// fp64 (relative error 2^-23 -> 2^-46 -> below fp64 rounding), a short dependent chain instead of a division
+__device__ __forceinline__ double recip(double a) {
+  double r = double(__frcp_rn(float(a)));
+  r = r * (2.0 - a * r);
+  r = r * (2.0 - a * r);
+  return r;
+}
 __device__ __forceinline__ double shfl_xor_f64(double v, int o) {
   return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o),
                           __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
 }
 
-struct ChanRec {  // one channel of one work item
-  double s, sx, sy;
-  float k;
-  float pad;
-};
-
-// walks the tiles of the work items a CTA owns: item = blockIdx.x, + gridDim.x, ...; the tiles of a
-// crop are split evenly over its `splits` items
-struct Cursor {
-  int item, t, t1;
-  __device__ __forceinline__ void open(int it, int n_items, int splits, int tiles) {
-    item = it;
-    if (it < n_items) {
-      const int sp = it % splits;
-      t = sp * tiles / splits;
-      t1 = (sp + 1) * tiles / splits;
-    } else { t = t1 = 0; }
-  }
-  __device__ __forceinline__ bool done(int n_items) const { return item >= n_items; }
-};
-
-// MAXT = 192: the common shapes (<= 192 threads per CTA) with up to three CTAs resident per SM
-template <int VEC, int LANES, bool F16, int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT <= 192 ? 3 : 1) softargmax_kernel(const SoftargmaxLaunch p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+// VEC channels per word, CH words per chunk; MAXT threads at most, MINB CTAs per SM
+template <int VEC, bool F16, int CH, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const SoftargmaxLaunch p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int V2 = VEC / 2;
   constexpr int esize = F16 ? 2 : 4;
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int slot = tid / LANES, lane = tid % LANES;
-  const bool live = slot < p.slots;                    // the last warp is padded with idle threads
+  constexpr int RAW = VEC * esize / 4;
+  const int tid = threadIdx.x;
   const int C = p.C, J = p.J, P = p.H * p.W;
+  const int lane_px = tid / p.slots, slot = tid - lane_px * p.slots;
+  const bool live = lane_px < p.lanes;                 // the last warp is padded with idle threads
   const int c0 = slot * VEC;
-  const int row_bytes = C * esize;
-  const int tile_bytes = p.ppc * row_bytes;
-  const int n_items = p.n * p.splits;
+  const int LC = p.lanes * C;
 
-  unsigned char *s_ring = smem_raw;                                              // [kStages][tile]
-  float2 *s_hw = reinterpret_cast<float2 *>(smem_raw + p.off_hw);                // [ppc] (row in tile, column)
-  ChanRec *s_ch = reinterpret_cast<ChanRec *>(smem_raw + p.off_ch);              // [C]
-  double *s_c01 = reinterpret_cast<double *>(s_ch + C);                          // [J][3]
-  uint64_t *full = reinterpret_cast<uint64_t *>(s_c01 + 3 * J);                  // [kStages]
+  float *s_k = reinterpret_cast<float *>(smem_raw);                              // [lanes][C] exponent
+  float *s_s = s_k + LC, *s_x = s_s + LC, *s_y = s_x + LC;                       // [lanes][C] sums
+  double *s_c01 = reinterpret_cast<double *>(s_y + LC);                          // [J][3] coordinates in mm
   __shared__ int s_is_last;
 
-  auto issue = [&](const Cursor &c, int stage) {     // thread 0 only
-    const int px0 = c.t * p.ppc;
-    const uint32_t bytes = uint32_t(min(p.ppc, P - px0)) * row_bytes;
-    const unsigned char *src = static_cast<const unsigned char *>(p.head) +
-                               (size_t(c.item / p.splits) * P + px0) * row_bytes;
-    ptx::mbar_arrive_expect_tx(full + stage, bytes);
-    ptx::bulk_load_1d(s_ring + size_t(stage) * tile_bytes, src, bytes, full + stage);
-  };
-  auto advance = [&](Cursor &c) {
-    if (++c.t >= c.t1) c.open(c.item + gridDim.x, n_items, p.splits, p.tiles);
+  const int item = blockIdx.x;
+  const int img = item / p.splits, split = item - img * p.splits;
+  const int px0 = split * p.ipx, px1 = min(P, px0 + p.ipx);
+  const int nchunks = (px1 - px0 + p.lanes * CH - 1) / (p.lanes * CH);
+
+  // running record of this thread's channels
+  float2 K2[V2], ts[V2], tx[V2], ty[V2];
+#pragma unroll
+  for (int v = 0; v < V2; ++v) {
+    K2[v] = make_float2(kNone, kNone);
+    ts[v] = tx[v] = ty[v] = make_float2(0.f, 0.f);
+  }
+  int pix = px0 + lane_px;                             // pixel of the next word to LOAD
+  const unsigned char *ptr = static_cast<const unsigned char *>(p.head) + ((size_t(img) * P + pix) * C + c0) * esize;
+  const size_t stride = size_t(p.lanes) * C * esize;
+  // (row, column) of the next word to COMPUTE, advanced by `lanes` pixels per word
+  float fh, fw;
+  {
+    const int h = pix / p.W;
+    fh = float(h); fw = float(pix - h * p.W);
+  }
+  const float Wf = float(p.W), dq = float(p.lanes / p.W), dr = float(p.lanes % p.W);
+  const float2 l2e = make_float2(kLog2e, kLog2e);
+
+  // one register buffer of CH words: a word is reloaded with the next chunk's data right after its last use,
+  // so the loads of chunk k+1 are in flight underneath the arithmetic of chunk k
+  Raw<RAW> buf[CH];
+  constexpr uint32_t kFill = F16 ? 0xfc00fc00u : 0xff800000u;      // -inf: a missing pixel adds exp(-inf) = 0
+  auto load_word = [&](Raw<RAW> &w, bool more) {
+    ldg_stream(w, ptr, int(more && live && pix < px1), kFill);
+    pix += p.lanes; ptr += stride;
   };
 
-  Cursor prod, cons;
-  cons.open(blockIdx.x, n_items, p.splits, p.tiles);
-  prod = cons;
-  if (tid == 0) {
-    for (int st = 0; st < p.stages; ++st) ptx::mbar_init(full + st, 1);
-    ptx::fence_mbar_init();
-  }
-  for (int q = tid; q < p.ppc; q += nthreads) {
-    const int h = q / p.W;
-    s_hw[q] = make_float2(float(h), float(q - h * p.W));
-  }
-  // programmatic dependent launch: the set-up above overlaps the tail of the kernel that produces the head
+  // programmatic dependent launch: everything above overlaps the tail of the kernel that produces the head
   // tensor (the logits convolution); nothing before this line touches global memory
+  const bool prof = p.prof != nullptr && tid == 0;
+  long long *stamp = p.prof + size_t(blockIdx.x) * 8;
+  if (prof) stamp[0] = clock64();
   ptx::griddep_wait();
   ptx::griddep_launch_dependents();
-  if (tid == 0) {
-    for (int st = 0; st < p.stages && !prod.done(n_items); ++st) { issue(prod, st); advance(prod); }
-  }
-  __syncthreads();                       // barriers initialised and the (row, column) table written
+  if (prof) stamp[1] = clock64();
 
-  // running record of this thread's channels over the current item
-  double S[VEC], SX[VEC], SY[VEC];
-  float K[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { S[v] = SX[v] = SY[v] = 0.0; K[v] = kNone; }
-  const float2 l2e = make_float2(kLog2e, kLog2e);
-  const uint32_t step_bytes = uint32_t(LANES) * row_bytes;
-  int stage = 0;
-  uint32_t phase = 0;
-
-  while (!cons.done(n_items)) {
-    const int px0 = cons.t * p.ppc;
-    const int steps = min(p.ppc, P - px0) / LANES;       // whole rows or an even part of one: a multiple of LANES
-    const int hh = px0 / p.W;
-    const float h0 = float(hh), w0 = float(px0 - hh * p.W);
-    ptx::mbar_wait_sleep(full + stage, phase);
-    if (live) {
-      const uint32_t base = ptx::smem_u32(s_ring) + uint32_t(stage) * tile_bytes + uint32_t(lane) * row_bytes + uint32_t(c0) * esize;
-      const int groups = steps / kGroup;
-      // pass 1: this thread's maximum per channel over the tile -> integer exponent
+  for (int i = 0; i < CH; ++i) load_word(buf[i], true);
+  for (int c = 0; c < nchunks; ++c) {
+    const bool more = c + 1 < nchunks;
+    // this chunk's maximum per channel -> integer exponent; raising it re-scales the running sums exactly
+    float2 nk[V2];
+    {
       float2 m[V2];
+      if constexpr (F16) {
+        // maximum on the raw half pairs (one HMNMX2 per two elements), widened once
+        __half2 mh[RAW];
 #pragma unroll
-      for (int v = 0; v < V2; ++v) m[v] = make_float2(-INFINITY, -INFINITY);
-      {
-        uint32_t a = base;
-        for (int g = 0; g < groups; ++g) {
+        for (int i = 0; i < CH; ++i) {
 #pragma unroll
-          for (int ii = 0; ii < kGroup; ++ii, a += step_bytes) {
-            float2 x[V2];
-            Vec<VEC, F16>::load(a, x);
-#pragma unroll
-            for (int v = 0; v < V2; ++v) { m[v].x = fmaxf(m[v].x, x[v].x); m[v].y = fmaxf(m[v].y, x[v].y); }
+          for (int v = 0; v < RAW; ++v) {
+            const __half2 xv = *reinterpret_cast<const __half2 *>(&buf[i].r[v]);
+            mh[v] = i ? __hmax2(mh[v], xv) : xv;
           }
         }
-        for (int i = groups * kGroup; i < steps; ++i, a += step_bytes) {
+#pragma unroll
+        for (int v = 0; v < V2; ++v) m[v] = __half22float2(mh[v]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
           float2 x[V2];
-          Vec<VEC, F16>::load(a, x);
+          unpack<RAW, F16, V2>(buf[i], x);
 #pragma unroll
-          for (int v = 0; v < V2; ++v) { m[v].x = fmaxf(m[v].x, x[v].x); m[v].y = fmaxf(m[v].y, x[v].y); }
-        }
-      }
-      float2 nk[V2];
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float kt = ceilf(((v & 1) ? m[v >> 1].y : m[v >> 1].x) * kLog2e);
-        if (kt > K[v]) {                                 // raise the exponent: exact re-scale of the running sums
-          const double r = pow2_neg(K[v] - kt);
-          S[v] *= r; SX[v] *= r; SY[v] *= r;
-          K[v] = kt;
-        }
-        if (v & 1) nk[v >> 1].y = -K[v]; else nk[v >> 1].x = -K[v];
-      }
-      // pass 2: exp once per element; fp32 partial sums of kGroup terms, then of groups
-      float2 ts[V2], tx[V2], ty[V2];
-#pragma unroll
-      for (int v = 0; v < V2; ++v) ts[v] = tx[v] = ty[v] = make_float2(0.f, 0.f);
-      uint32_t a = base;
-      uint32_t hwa = ptx::smem_u32(s_hw) + uint32_t(lane) * 8;
-      auto step = [&](uint32_t xa, uint32_t ha, float2 (&gs)[V2], float2 (&gx)[V2], float2 (&gy)[V2]) {
-        float2 x[V2];
-        Vec<VEC, F16>::load(xa, x);
-        const float2 rc = ptx::lds_v2(ha);
-        const float fh = rc.x + h0, fw = rc.y + w0;
-        const float2 fh2 = make_float2(fh, fh), fw2 = make_float2(fw, fw);
-#pragma unroll
-        for (int v = 0; v < V2; ++v) {
-          const float2 t = __ffma2_rn(x[v], l2e, nk[v]);
-          const float2 e = make_float2(ptx::ex2_approx(t.x), ptx::ex2_approx(t.y));
-          gs[v] = __fadd2_rn(gs[v], e);
-          gx[v] = __ffma2_rn(e, fw2, gx[v]);
-          gy[v] = __ffma2_rn(e, fh2, gy[v]);
-        }
-      };
-      for (int g = 0; g < groups; ++g, hwa += kGroup * LANES * 8) {
-        float2 gs[V2], gx[V2], gy[V2];
-#pragma unroll
-        for (int v = 0; v < V2; ++v) gs[v] = gx[v] = gy[v] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int ii = 0; ii < kGroup; ++ii, a += step_bytes) step(a, hwa + ii * LANES * 8, gs, gx, gy);
-#pragma unroll
-        for (int v = 0; v < V2; ++v) {
-          ts[v] = __fadd2_rn(ts[v], gs[v]); tx[v] = __fadd2_rn(tx[v], gx[v]); ty[v] = __fadd2_rn(ty[v], gy[v]);
-        }
-      }
-      if (groups * kGroup < steps) {
-        float2 gs[V2], gx[V2], gy[V2];
-#pragma unroll
-        for (int v = 0; v < V2; ++v) gs[v] = gx[v] = gy[v] = make_float2(0.f, 0.f);
-        for (int i = groups * kGroup; i < steps; ++i, a += step_bytes, hwa += LANES * 8) step(a, hwa, gs, gx, gy);
-#pragma unroll
-        for (int v = 0; v < V2; ++v) {
-          ts[v] = __fadd2_rn(ts[v], gs[v]); tx[v] = __fadd2_rn(tx[v], gx[v]); ty[v] = __fadd2_rn(ty[v], gy[v]);
+          for (int v = 0; v < V2; ++v) {
+            m[v].x = i ? fmaxf(m[v].x, x[v].x) : x[v].x;
+            m[v].y = i ? fmaxf(m[v].y, x[v].y) : x[v].y;
+          }
         }
       }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        S[v] += double((v & 1) ? ts[v >> 1].y : ts[v >> 1].x);
-        SX[v] += double((v & 1) ? tx[v >> 1].y : tx[v >> 1].x);
-        SY[v] += double((v & 1) ? ty[v >> 1].y : ty[v >> 1].x);
+      for (int v = 0; v < V2; ++v) {
+        const float2 kn = make_float2(fmaxf(K2[v].x, ceilf(m[v].x * kLog2e)), fmaxf(K2[v].y, ceilf(m[v].y * kLog2e)));
+        const float2 r = make_float2(pow2_neg_f32(K2[v].x - kn.x), pow2_neg_f32(K2[v].y - kn.y));
+        ts[v] = __fmul2_rn(ts[v], r); tx[v] = __fmul2_rn(tx[v], r); ty[v] = __fmul2_rn(ty[v], r);
+        K2[v] = kn;
+        nk[v] = make_float2(-kn.x, -kn.y);
       }
     }
-    __syncthreads();                     // every thread is done with this ring stage
-    if (tid == 0 && !prod.done(n_items)) { issue(prod, stage); advance(prod); }
-    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-    const int item = cons.item;
-    const bool item_done = (cons.t + 1 >= cons.t1);
-    advance(cons);
-    if (!item_done) continue;
+    float2 gs[V2], gx[V2], gy[V2];
+#pragma unroll
+    for (int v = 0; v < V2; ++v) gs[v] = gx[v] = gy[v] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      float2 x[V2];
+      unpack<RAW, F16, V2>(buf[i], x);
+      load_word(buf[i], more);
+      const float2 fh2 = make_float2(fh, fh), fw2 = make_float2(fw, fw);
+#pragma unroll
+      for (int v = 0; v < V2; ++v) {
+        const float2 t = __ffma2_rn(x[v], l2e, nk[v]);
+        const float2 e = make_float2(ptx::ex2_approx(t.x), ptx::ex2_approx(t.y));
+        gs[v] = __fadd2_rn(gs[v], e);
+        gx[v] = __ffma2_rn(e, fw2, gx[v]);
+        gy[v] = __ffma2_rn(e, fh2, gy[v]);
+      }
+      fw += dr; fh += dq;
+      if (fw >= Wf) { fw -= Wf; fh += 1.f; }
+    }
+#pragma unroll
+    for (int v = 0; v < V2; ++v) {
+      ts[v] = __fadd2_rn(ts[v], gs[v]); tx[v] = __fadd2_rn(tx[v], gx[v]); ty[v] = __fadd2_rn(ty[v], gy[v]);
+    }
+  }
 
-    // ======================= end of a work item: merge and publish =======================
-    const int img = item / p.splits, split = item - img * p.splits;
-    // pixel lanes -> channel: the lanes of a slot sit in one warp; exact re-scaling, fp64 sums
+  if (prof) stamp[2] = clock64();
+  // ======================= per-thread records -> shared memory =======================
+  if (live) {
+    const int o = lane_px * C + c0;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      float kk = K[v];
+    for (int v = 0; v < V2; ++v) {
+      *reinterpret_cast<float2 *>(s_k + o + 2 * v) = K2[v];
+      *reinterpret_cast<float2 *>(s_s + o + 2 * v) = ts[v];
+      *reinterpret_cast<float2 *>(s_x + o + 2 * v) = tx[v];
+      *reinterpret_cast<float2 *>(s_y + o + 2 * v) = ty[v];
+    }
+  }
+  __syncthreads();
+  if (prof) stamp[3] = clock64();
+  // lanes x depth -> joint in one stage: `tpj` adjacent threads per joint (a power of two, all warps busy), each
+  // takes its share of the joint's D x lanes records -- exact power-of-two weights, fp64 sums -- and a butterfly
+  // over the tpj threads finishes the sum
+  if (p.D == 8 && p.lanes == 8 && p.tpj == 16) {
+    // the shape every reference configuration has (depth 8, 8 pixel lanes, 16 threads per joint): thread i of a
+    // joint owns depth i & 7 and lanes (i >> 3) + {0, 2, 4, 6}; everything unrolled, one reciprocal per joint
+    const int t_end = (J * 16 + 31) & ~31;
+    for (int t = tid; t < t_end; t += blockDim.x) {
+      const int j = t >> 4, i = t & 15, d = i & 7;
+      const bool has = j < J;
+      const int base = has ? (i >> 3) * C + d * J + j : 0;
+      float k4[4], s4[4], x4[4], y4[4];
 #pragma unroll
-      for (int o = LANES / 2; o >= 1; o >>= 1) kk = fmaxf(kk, __shfl_xor_sync(0xffffffffu, kk, o));
-      const double wgt = pow2_neg(K[v] - kk);
-      double a = wgt * S[v], ax = wgt * SX[v], ay = wgt * SY[v];
-#pragma unroll
-      for (int o = LANES / 2; o >= 1; o >>= 1) {
-        a += shfl_xor_f64(a, o); ax += shfl_xor_f64(ax, o); ay += shfl_xor_f64(ay, o);
+      for (int q = 0; q < 4; ++q) {
+        const int idx = base + q * 2 * C;
+        k4[q] = s_k[idx]; s4[q] = s_s[idx]; x4[q] = s_x[idx]; y4[q] = s_y[idx];
       }
-      if (live && lane == 0) {
-        ChanRec o; o.s = a; o.sx = ax; o.sy = ay; o.k = kk; o.pad = 0.f;
-        s_ch[c0 + v] = o;
+      float km = has ? fmaxf(fmaxf(k4[0], k4[1]), fmaxf(k4[2], k4[3])) : kNone;
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) km = fmaxf(km, __shfl_xor_sync(0xffffffffu, km, o));
+      double a4[4], ax4[4], ay4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float wgt = has ? pow2_neg_f32(k4[q] - km) : 0.f;    // a scale by 2^-d is exact short of underflow
+        a4[q] = double(wgt * s4[q]); ax4[q] = double(wgt * x4[q]); ay4[q] = double(wgt * y4[q]);
       }
-      S[v] = SX[v] = SY[v] = 0.0; K[v] = kNone;        // reset for the next item
+      double a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+      double ax = (ax4[0] + ax4[1]) + (ax4[2] + ax4[3]);
+      double ay = (ay4[0] + ay4[1]) + (ay4[2] + ay4[3]);
+      double az = double(d) * a;
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) {
+        a += shfl_xor_f64(a, o); ax += shfl_xor_f64(ax, o); ay += shfl_xor_f64(ay, o); az += shfl_xor_f64(az, o);
+      }
+      if (has && i == 0) {
+        if (p.splits > 1) {
+          double *rec = p.partials + ((size_t(img) * p.splits + split) * J + j) * 5;
+          rec[0] = double(km); rec[1] = a; rec[2] = ax; rec[3] = ay; rec[4] = az;
+        } else {
+          const double inv = recip(a);
+          s_c01[3 * j] = ax * inv * p.mul_x;
+          s_c01[3 * j + 1] = ay * inv * p.mul_y;
+          s_c01[3 * j + 2] = az * inv * p.mul_z;
+        }
+      }
+    }
+  } else {
+    const int tpj = p.tpj, nrec = p.D * p.lanes;
+    const int t_end = (J * tpj + 31) & ~31;                      // whole warps: every lane of a shuffle takes part
+    const int step_l = tpj / p.D, step_d = tpj - step_l * p.D;
+    for (int t = tid; t < t_end; t += blockDim.x) {
+      const int j = t / tpj, i = t - j * tpj;
+      const bool has = j < J;
+      const int l0 = i / p.D, d0 = i - l0 * p.D;
+      float km = kNone;
+      if (has) {
+        int l = l0, d = d0;
+        for (int r = i; r < nrec; r += tpj) {
+          km = fmaxf(km, s_k[l * C + d * J + j]);
+          l += step_l; d += step_d;
+          if (d >= p.D) { d -= p.D; ++l; }
+        }
+      }
+      for (int o = tpj >> 1; o >= 1; o >>= 1) km = fmaxf(km, __shfl_xor_sync(0xffffffffu, km, o));
+      double a = 0.0, ax = 0.0, ay = 0.0, az = 0.0;
+      if (has) {
+        int l = l0, d = d0;
+        for (int r = i; r < nrec; r += tpj) {
+          const int idx = l * C + d * J + j;
+          const float wgt = pow2_neg_f32(s_k[idx] - km);         // a scale by 2^-d is exact short of underflow
+          const double sv = double(wgt * s_s[idx]);
+          a += sv; ax += double(wgt * s_x[idx]); ay += double(wgt * s_y[idx]); az += double(d) * sv;
+          l += step_l; d += step_d;
+          if (d >= p.D) { d -= p.D; ++l; }
+        }
+      }
+      for (int o = tpj >> 1; o >= 1; o >>= 1) {
+        a += shfl_xor_f64(a, o); ax += shfl_xor_f64(ax, o); ay += shfl_xor_f64(ay, o); az += shfl_xor_f64(az, o);
+      }
+      if (has && i == 0) {
+        if (p.splits > 1) {
+          double *rec = p.partials + ((size_t(img) * p.splits + split) * J + j) * 5;
+          rec[0] = double(km); rec[1] = a; rec[2] = ax; rec[3] = ay; rec[4] = az;
+        } else {
+          // expectation of linspace(0,1,n) along each axis == E[index]/(n-1); mul_* carry 1/(n-1) and mm
+          const double inv = recip(a);
+          s_c01[3 * j] = ax * inv * p.mul_x;
+          s_c01[3 * j + 1] = ay * inv * p.mul_y;
+          s_c01[3 * j + 2] = az * inv * p.mul_z;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (prof) stamp[4] = clock64();
+  if (p.splits > 1) {
+    // the last CTA of the crop merges the per-split records.  bar.sync above orders the J writers before
+    // thread 0, whose gpu-scope fence is cumulative over what it has observed.
+    if (tid == 0) {
+      __threadfence();
+      const unsigned int ticket = atomicAdd(p.counters + img, 1u);
+      s_is_last = (ticket == unsigned(p.splits - 1));
+      if (s_is_last) {
+        __threadfence();
+        p.counters[img] = 0;                           // self-cleaning for the next launch
+      }
     }
     __syncthreads();
-    // depth -> joint
-    double TS = 0.0, TX = 0.0, TY = 0.0, TZ = 0.0;
-    float TK = kNone;
+    if (!s_is_last) return;
     if (tid < J) {
-      for (int d = 0; d < p.D; ++d) TK = fmaxf(TK, s_ch[d * J + tid].k);
-      for (int d = 0; d < p.D; ++d) {
-        const ChanRec r = s_ch[d * J + tid];
-        const double wgt = pow2_neg(r.k - TK);
-        TS += wgt * r.s; TX += wgt * r.sx; TY += wgt * r.sy; TZ += double(d) * (wgt * r.s);
+      const double *recs = p.partials + (size_t(img) * p.splits) * J * 5;
+      double gk = double(kNone);
+      for (int sp = 0; sp < p.splits; ++sp) gk = fmax(gk, __ldcg(recs + (size_t(sp) * J + tid) * 5));
+      double TS = 0.0, TX = 0.0, TY = 0.0, TZ = 0.0;
+      for (int sp = 0; sp < p.splits; ++sp) {
+        const double *rec = recs + (size_t(sp) * J + tid) * 5;
+        const double wgt = pow2_neg(float(__ldcg(rec) - gk));
+        TS += wgt * __ldcg(rec + 1); TX += wgt * __ldcg(rec + 2);
+        TY += wgt * __ldcg(rec + 3); TZ += wgt * __ldcg(rec + 4);
       }
+      const double inv = recip(TS);
+      s_c01[3 * tid] = TX * inv * p.mul_x;
+      s_c01[3 * tid + 1] = TY * inv * p.mul_y;
+      s_c01[3 * tid + 2] = TZ * inv * p.mul_z;
     }
-    bool publish = true;
-    if (p.splits > 1) {
-      // publish this split's record; the last CTA of the crop merges them.  bar.sync orders the J
-      // writers before thread 0, whose gpu-scope fence is cumulative over what it has observed.
-      if (tid < J) {
-        double *rec = p.partials + ((size_t(img) * p.splits + split) * J + tid) * 5;
-        rec[0] = double(TK); rec[1] = TS; rec[2] = TX; rec[3] = TY; rec[4] = TZ;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        const unsigned int ticket = atomicAdd(p.counters + img, 1u);
-        s_is_last = (ticket == unsigned(p.splits - 1));
-        if (s_is_last) __threadfence();
-      }
-      __syncthreads();
-      publish = s_is_last != 0;
-      if (publish && tid < J) {
-        const double *recs = p.partials + (size_t(img) * p.splits) * J * 5;
-        double gk = double(kNone);
-        for (int sp = 0; sp < p.splits; ++sp) gk = fmax(gk, __ldcg(recs + (size_t(sp) * J + tid) * 5));
-        TS = TX = TY = TZ = 0.0;
-        for (int sp = 0; sp < p.splits; ++sp) {
-          const double *rec = recs + (size_t(sp) * J + tid) * 5;
-          const double wgt = pow2_neg(float(__ldcg(rec) - gk));
-          TS += wgt * __ldcg(rec + 1); TX += wgt * __ldcg(rec + 2);
-          TY += wgt * __ldcg(rec + 3); TZ += wgt * __ldcg(rec + 4);
-        }
-      }
-      if (publish && tid == 0) p.counters[img] = 0;   // self-cleaning for the next launch
-    }
-    if (publish) {
-      // expectation of linspace(0,1,n) along each axis == E[index]/(n-1); mul_* carry 1/(n-1) and mm
-      if (tid < J) {
-        const double inv = 1.0 / TS;
-        s_c01[3 * tid] = TX * inv * p.mul_x;
-        s_c01[3 * tid + 1] = TY * inv * p.mul_y;
-        s_c01[3 * tid + 2] = TZ * inv * p.mul_z;
-      }
-      __syncthreads();
-      for (int i = tid; i < p.n_out * 3; i += nthreads) {
-        const int jo = i / 3, a = i - 3 * jo;
-        p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
-      }
-    }
-    __syncthreads();                     // s_ch / s_c01 / s_is_last are reused by the next item
+    __syncthreads();
   }
+  for (int i = tid; i < p.n_out * 3; i += blockDim.x) {
+    const int jo = i / 3, a = i - 3 * jo;
+    p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
+  }
+  if (prof) stamp[5] = clock64();
 }
-
-size_t tile_bytes(const SoftargmaxLaunch &L) {
-  return (size_t(L.ppc) * L.C * (L.head_f16 ? 2 : 4) + 127) & ~size_t(127);
-}
-size_t hw_bytes(const SoftargmaxLaunch &L) { return (size_t(L.ppc) * 8 + 127) & ~size_t(127); }
 
 size_t smem_bytes(const SoftargmaxLaunch &L) {
-  return L.stages * tile_bytes(L) + hw_bytes(L) + size_t(L.C) * sizeof(ChanRec) + size_t(3) * L.J * 8 + kMaxStages * 8 + 16;
+  return size_t(4) * L.lanes * L.C * sizeof(float) + size_t(3) * L.J * sizeof(double) + 16;
 }
 
-template <int VEC, int LANES, bool F16, int MAXT>
+template <int VEC, bool F16, int CH, int MAXT, int MINB>
 metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
   static size_t configured = 0;
   const size_t sm = smem_bytes(L);
   if (configured < sm) {
-    METRO_CUDA(cudaFuncSetAttribute(softargmax_kernel<VEC, LANES, F16, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+    METRO_CUDA(cudaFuncSetAttribute(softargmax_kernel<VEC, F16, CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = 100 * 1024;
   }
-  const int n_items = L.n * L.splits;
-  const dim3 grid(unsigned(n_items < L.max_ctas ? n_items : L.max_ctas)), block(unsigned((L.slots * L.lanes + 31) & ~31));
+  const dim3 grid(unsigned(L.n) * unsigned(L.splits)), block(unsigned((L.slots * L.lanes + 31) & ~31));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = sm; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  METRO_CUDA(cudaLaunchKernelEx(&cfg, softargmax_kernel<VEC, LANES, F16, MAXT>, L));
+  static const bool want_prof = std::getenv("METRO_SAM_PROF") != nullptr;
+  if (!want_prof) {
+    METRO_CUDA(cudaLaunchKernelEx(&cfg, softargmax_kernel<VEC, F16, CH, MAXT, MINB>, L));
+    return METRO_OK;
+  }
+  // debug: per-CTA phase durations in SM clocks (launch -> dependency wait -> stream -> records -> merge -> output)
+  SoftargmaxLaunch P = L;
+  const size_t n_ctas = size_t(grid.x);
+  METRO_CUDA(cudaMalloc(&P.prof, n_ctas * 8 * sizeof(long long)));
+  METRO_CUDA(cudaMemsetAsync(P.prof, 0, n_ctas * 8 * sizeof(long long), stream));
+  METRO_CUDA(cudaLaunchKernelEx(&cfg, softargmax_kernel<VEC, F16, CH, MAXT, MINB>, P));
+  METRO_CUDA(cudaStreamSynchronize(stream));
+  std::vector<long long> hst(n_ctas * 8);
+  METRO_CUDA(cudaMemcpy(hst.data(), P.prof, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  METRO_CUDA(cudaFree(P.prof));
+  double sum[5] = {0, 0, 0, 0, 0}, mx[5] = {0, 0, 0, 0, 0};
+  for (size_t c = 0; c < n_ctas; ++c)
+    for (int i = 0; i < 5; ++i) {
+      const double d = double(hst[c * 8 + i + 1] - hst[c * 8 + i]);
+      sum[i] += d; if (d > mx[i]) mx[i] = d;
+    }
+  std::fprintf(stderr, "[metro sam prof] %zu CTAs x %u threads, cycles avg/max: wait %.0f/%.0f stream %.0f/%.0f records %.0f/%.0f merge %.0f/%.0f out %.0f/%.0f\n",
+               n_ctas, block.x, sum[0] / n_ctas, mx[0], sum[1] / n_ctas, mx[1], sum[2] / n_ctas, mx[2], sum[3] / n_ctas, mx[3],
+               sum[4] / n_ctas, mx[4]);
   return METRO_OK;
 }
 
@@ -399,8 +445,10 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   // count is not a multiple of that
   const bool f16 = d.head_dtype == METRO_F16;
   if (d.word_bytes != 0 && d.word_bytes != 8 && d.word_bytes != 16) return fail(METRO_ERR_VALUE, "softargmax: word_bytes must be 0, 8 or 16");
-  int vec = (d.word_bytes == 8 ? 8 : 16) / (f16 ? 2 : 4);
-  if (d.word_bytes == 0 && (d.n_joints_model * d.depth) % vec != 0) vec /= 2;
+  // fp16 heads default to 8-byte words: twice the threads per byte, the decode of a half-width head being
+  // bound by the exp per element rather than by HBM
+  int vec = (d.word_bytes == 8 || (d.word_bytes == 0 && f16) ? 8 : 16) / (f16 ? 2 : 4);
+  if (d.word_bytes == 0 && (d.n_joints_model * d.depth) % vec != 0 && vec * (f16 ? 2 : 4) == 16) vec /= 2;
   if (d.head_dtype != METRO_F16 && d.head_dtype != METRO_F32) return fail(METRO_ERR_VALUE, "softargmax: bad head_dtype");
   L = SoftargmaxLaunch();
   L.n = n; L.H = L.W = d.side; L.J = d.n_joints_model; L.D = d.depth; L.C = L.J * L.D;
@@ -424,54 +472,38 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   L.vec = vec;
   if (L.slots > kMaxThreads) return fail(METRO_ERR_VALUE, "softargmax: too many head channels (%d)", L.C);
   const int P = L.H * L.W;
-  // CTA shape: `slots` 16-byte channel slots x `lanes` pixel lanes (a power of two dividing W, so whole
-  // rows split evenly over the lanes and the lanes of a slot share a warp).  Tiles are whole rows,
-  // ~35 KB; a 2-stage ring per CTA and 2-3 CTAs per SM keep ~150 KB of copies in flight per SM.
-  int lanes = d.lanes > 0 ? d.lanes : 4;
-  while (lanes > 1 && (lanes > 8 || (lanes & (lanes - 1)) != 0 || L.W % lanes != 0 ||
-                       ((L.slots * lanes + 31) & ~31) > kMaxThreads)) --lanes;
+  // CTA shape: `slots` channel slots x `lanes` pixel lanes (a power of two): the smallest that gives the CTA
+  // at least 256 threads, so that two resident CTAs put ~18 warps on an SM
+  int lanes = 1;
+  if (d.lanes > 0) {
+    while (lanes * 2 <= d.lanes && lanes < 32) lanes *= 2;   // rounded down to a power of two
+  } else {
+    while (lanes < 32 && L.slots * lanes < 256) lanes *= 2;
+  }
+  while (lanes > 1 && ((L.slots * lanes + 31) & ~31) > kMaxThreads) lanes /= 2;
   if (((L.slots * lanes + 31) & ~31) > kMaxThreads) return fail(METRO_ERR_VALUE, "softargmax: too many head channels (%d)", L.C);
   L.lanes = lanes;
-  const int row_bytes = L.C * (L.head_f16 ? 2 : 4);
-  // tile: ~36 KB of whole rows, or an even part of one row when a row is larger than that (measured on
-  // B200: larger tiles amortise the per-tile bookkeeping better than more resident CTAs hide latency)
-  // ring: `stages` tiles of ~`tile_kb` KB in flight per CTA (tunable for experiments: METRO_SAM_STAGES / METRO_SAM_TILE_KB)
-  int tile_kb = 40;
-  L.stages = 2;
-  if (const char *e = getenv("METRO_SAM_STAGES")) L.stages = atoi(e);
-  if (const char *e = getenv("METRO_SAM_TILE_KB")) tile_kb = atoi(e);
-  if (L.stages < 2) L.stages = 2;
-  if (L.stages > kMaxStages) L.stages = kMaxStages;
-  const int budget_px = (tile_kb * 1024) / row_bytes;
-  int ppc;
-  if (budget_px >= L.W) {
-    int rows = budget_px / L.W;
-    if (rows > kMaxSteps * lanes / L.W) rows = kMaxSteps * lanes / L.W;   // bounded per-thread partial sums
-    if (rows > L.H) rows = L.H;
-    if (rows < 1) rows = 1;
-    ppc = rows * L.W;
-    L.tiles = (L.H + rows - 1) / rows;
-  } else {
-    int parts = 1;
-    while (L.W % (parts * 2) == 0 && (L.W / (parts * 2)) % lanes == 0 && L.W / parts > budget_px) parts *= 2;
-    ppc = L.W / parts;
-    if (size_t(ppc) * row_bytes > 90 * 1024) return fail(METRO_ERR_VALUE, "softargmax: a heatmap row of %d bytes cannot be tiled", row_bytes * L.W);
-    L.tiles = L.H * parts;
+  {
+    // threads per joint in the merge: the largest power of two <= 32 that the CTA's threads cover for all joints
+    const int threads = (L.slots * lanes + 31) & ~31;
+    L.tpj = 32;
+    while (L.tpj > 1 && L.J * L.tpj > threads) L.tpj /= 2;
   }
-  L.ppc = ppc;
-  // work items: one per crop, or -- for large heatmaps -- a fixed number of row ranges per crop that
-  // depends on the heatmap shape ONLY, so a crop's result is bit-identical whatever batch or GPU shard it
-  // is part of (merged by the last CTA of the crop to finish)
-  int splits = d.splits > 0 ? d.splits : L.tiles / 8;
-  if (splits > 4 && d.splits <= 0) splits = 4;
+  // work items: one per crop, or -- for large heatmaps -- up to four row-major pixel ranges of >= 256 pixels
+  // (a CTA lives ~3 us beyond its streaming time, so items must be long; four per crop keep a 64-crop shard
+  // of 32x32 heatmaps at one full wave of CTAs).  The number of ranges depends on the heatmap shape ONLY, so
+  // a crop's result is bit-identical whatever batch or GPU shard it is part of (merged by the last CTA of the
+  // crop to finish)
+  int item_px = kItemPixels, max_splits = 4;
+  if (const char *e = getenv("METRO_SAM_ITEM_PX")) item_px = atoi(e) > 0 ? atoi(e) : item_px;
+  if (const char *e = getenv("METRO_SAM_MAX_SPLITS")) max_splits = atoi(e) > 0 ? atoi(e) : max_splits;
+  int splits = d.splits > 0 ? d.splits : (P + item_px - 1) / item_px;
+  if (d.splits <= 0 && splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  if (splits > L.tiles) splits = L.tiles;
-  L.splits = splits;
-  L.max_ctas = 148 * 3;
-  L.rpt = L.ppc / lanes;
-  L.off_hw = int(L.stages * tile_bytes(L));
-  L.off_ch = L.off_hw + int(hw_bytes(L));
-  if (smem_bytes(L) > 200 * 1024) return fail(METRO_ERR_VALUE, "softargmax: shared memory budget exceeded");
+  if (splits > P) splits = P;
+  L.ipx = (P + splits - 1) / splits;
+  L.splits = (P + L.ipx - 1) / L.ipx;              // no empty item
+  if (smem_bytes(L) > 100 * 1024) return fail(METRO_ERR_VALUE, "softargmax: shared memory budget exceeded");
   return METRO_OK;
 }
 
@@ -483,22 +515,15 @@ size_t softargmax_workspace_bytes(const SoftargmaxLaunch &L) {
 metro_status softargmax_launch(const SoftargmaxLaunch &L, cudaStream_t stream) {
   if (L.n == 0) return METRO_OK;
   const int threads = (L.slots * L.lanes + 31) & ~31;
-#define METRO_SAM(V, LN, H) return (threads <= 192 ? launch_t<V, LN, H, 192>(L, stream) : launch_t<V, LN, H, kMaxThreads>(L, stream))
-#define METRO_SAM_LANES(V, H)        \
-  switch (L.lanes) {                 \
-    case 1: METRO_SAM(V, 1, H);      \
-    case 2: METRO_SAM(V, 2, H);      \
-    case 4: METRO_SAM(V, 4, H);      \
-    case 8: METRO_SAM(V, 8, H);      \
-  }
+  // two CTAs per SM for the common shapes (<= 304 threads: 19 joints x 8 depths, 16-byte words, 8 lanes), one for wider ones
+#define METRO_SAM(V, H, CH) return (threads <= 304 ? launch_t<V, H, CH, 304, 2>(L, stream) : launch_t<V, H, CH, kMaxThreads, 1>(L, stream))
   if (L.head_f16) {
-    if (L.vec == 8) { METRO_SAM_LANES(8, true) } else { METRO_SAM_LANES(4, true) }
+    if (L.vec == 8) { METRO_SAM(8, true, 4); } else { METRO_SAM(4, true, 8); }
   } else {
-    if (L.vec == 4) { METRO_SAM_LANES(4, false) } else { METRO_SAM_LANES(2, false) }
+    if (L.vec == 4) { METRO_SAM(4, false, 8); } else { METRO_SAM(2, false, 8); }
   }
-#undef METRO_SAM_LANES
 #undef METRO_SAM
-  return fail(METRO_ERR_INTERNAL, "softargmax: %d lanes not instantiated", L.lanes);
+  return fail(METRO_ERR_INTERNAL, "softargmax: no kernel for this word size");
 }
 
 }  // namespace metro
