@@ -333,8 +333,14 @@ def main():
     sam_us = s0.elapsed_time(s1) / (iters * reps_g) * 1e3
     sam_bytes = spec.softargmax_bytes_per_crop(len(perm), isz) * n
     sam_gbs = sam_bytes / (sam_us * 1e-6) / 1e9
+    sam_traffic = None
+    if os.path.exists(tpath) and n == cfg_batch // max(cfg_gpus, 1):
+        try:
+            sam_traffic = json.load(open(tpath)).get('softargmax_dram_bytes_per_launch')
+        except Exception:
+            sam_traffic = None
     roofline_sam = {'kernel': 'softargmax_kernel', 'bound': 'hbm', 'achieved': sam_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': sam_gbs / hbm_peak, 'traffic': None, 'us_per_launch': sam_us, 'bytes_per_launch': sam_bytes,
+                    'frac': sam_gbs / hbm_peak, 'traffic': sam_traffic, 'us_per_launch': sam_us, 'bytes_per_launch': sam_bytes,
                     'note': f'{n_rot} rotating inputs ({n_rot * sam_bytes / 1e6:.0f} MB > L2), back-to-back launches replayed from a CUDA graph'}
 
     # ---- CPU baseline beside it (bounded sample; reported, not the target) ----

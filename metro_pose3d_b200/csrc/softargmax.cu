@@ -364,14 +364,33 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
     if (!s_is_last) return;
     if (tid < J) {
       const double *recs = p.partials + (size_t(img) * p.splits) * J * 5;
-      double gk = double(kNone);
-      for (int sp = 0; sp < p.splits; ++sp) gk = fmax(gk, __ldcg(recs + (size_t(sp) * J + tid) * 5));
       double TS = 0.0, TX = 0.0, TY = 0.0, TZ = 0.0;
-      for (int sp = 0; sp < p.splits; ++sp) {
-        const double *rec = recs + (size_t(sp) * J + tid) * 5;
-        const double wgt = pow2_neg(float(__ldcg(rec) - gk));
-        TS += wgt * __ldcg(rec + 1); TX += wgt * __ldcg(rec + 2);
-        TY += wgt * __ldcg(rec + 3); TZ += wgt * __ldcg(rec + 4);
+      if (p.splits <= 4) {
+        // all records in flight at once (one L2 round trip instead of two dependent passes)
+        double r[4][5];
+#pragma unroll
+        for (int sp = 0; sp < 4; ++sp) {
+          const double *rec = recs + (size_t(sp < p.splits ? sp : 0) * J + tid) * 5;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) r[sp][q] = __ldcg(rec + q);
+        }
+        double gk = r[0][0];
+#pragma unroll
+        for (int sp = 1; sp < 4; ++sp) gk = sp < p.splits ? fmax(gk, r[sp][0]) : gk;
+#pragma unroll
+        for (int sp = 0; sp < 4; ++sp) {
+          const double wgt = sp < p.splits ? pow2_neg(float(r[sp][0] - gk)) : 0.0;
+          TS += wgt * r[sp][1]; TX += wgt * r[sp][2]; TY += wgt * r[sp][3]; TZ += wgt * r[sp][4];
+        }
+      } else {
+        double gk = double(kNone);
+        for (int sp = 0; sp < p.splits; ++sp) gk = fmax(gk, __ldcg(recs + (size_t(sp) * J + tid) * 5));
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const double *rec = recs + (size_t(sp) * J + tid) * 5;
+          const double wgt = pow2_neg(float(__ldcg(rec) - gk));
+          TS += wgt * __ldcg(rec + 1); TX += wgt * __ldcg(rec + 2);
+          TY += wgt * __ldcg(rec + 3); TZ += wgt * __ldcg(rec + 4);
+        }
       }
       const double inv = recip(TS);
       s_c01[3 * tid] = TX * inv * p.mul_x;
