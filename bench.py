@@ -257,6 +257,18 @@ def main():
         e2e_ms = float(t.item())
     e2e = {'value': n * world / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(host_in.numel() * 4),
            'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': e2e_ms}
+    # the same call fed uint8 crops (metro_infer_host_u8): extra information, not the headline
+    e2e_u8 = None
+    if world == 1:
+        host_u8 = torch.randint(0, 256, (n, 256, 256, 3), dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            model.infer_host(host_u8, host_out)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            model.infer_host(host_u8, host_out)
+        u8_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        e2e_u8 = {'value': n / (u8_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(host_u8.numel()),
+                  'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': u8_ms}
 
     if rank != 0:
         if world > 1:
@@ -361,7 +373,7 @@ def main():
                    'arithmetic': 'f16 operands (the reference default, src/options.py:73), f32 accumulate, f32 head and decode',
                    'head_dtype': args.head_dtype, 'gflop_per_crop': spec.flops_per_crop / 1e9,
                    'tensor_frac_whole_step': spec.flops_per_crop * n / (ms * 1e-3) / 1e12 / tf_sust},
-        'e2e': e2e, 'gpu_launches': model.launch_count(n) * args.steps,
+        'e2e': e2e, 'e2e_u8': e2e_u8, 'gpu_launches': model.launch_count(n) * args.steps,
         'roofline': roofline, 'roofline_softargmax': roofline_sam, 'cpu_baseline': cpu, 'clocks': clocks,
     }
     print(json.dumps(line), flush=True)

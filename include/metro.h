@@ -97,6 +97,11 @@ metro_status metro_infer_host(metro_handle *h, const float *images_host, int32_t
  * kernel).  images_u8_dev: device uint8 NHWC [n,256,256,3]. */
 metro_status metro_infer_u8(metro_handle *h, const uint8_t *images_u8_dev, int32_t n,
                             float *poses_dev, void *stream);
+/* The same through HOST buffers: uint8 crops as the reference's loader holds them before
+ * src/data/data_loading.py:102-103 / src/improc.py:56-61 turn them into floats -- a quarter of the
+ * PCIe bytes of metro_infer_host. */
+metro_status metro_infer_host_u8(metro_handle *h, const uint8_t *images_u8_host, int32_t n,
+                                 float *poses_host);
 
 /* ---- stand-alone soft-argmax: replaces net_output_to_heatmap_and_coords + heatmap_to_metric +
  *      root_relative + gather (volumetric.py:227-235,288-306; tfu.py:466-499; tfu3d.py:23-25;

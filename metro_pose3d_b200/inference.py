@@ -108,21 +108,22 @@ class MetroModel:
         return out
 
     def infer_host(self, images: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """Host buffers in / out (what ``sess.run`` does for numpy feeds, inference.py:26-27)."""
+        """Host buffers in / out (what ``sess.run`` does for numpy feeds, inference.py:26-27).  uint8 crops
+        (the loader's format before improc.py:56-61) go through ``metro_infer_host_u8``: a quarter of the bytes."""
         if hasattr(images, 'numpy'):            # CPU torch tensor (possibly pinned): zero-copy view
             images = images.numpy()
         if images.ndim != 4 or images.shape[1:] != (self.spec.proc_side, self.spec.proc_side, 3):
             raise ValueError(f'expected [N,{self.spec.proc_side},{self.spec.proc_side},3] NHWC, got {images.shape}')
-        if images.dtype != np.float32:
-            raise ValueError(f'expected float32 images, got {images.dtype}')
+        if images.dtype not in (np.float32, np.uint8):
+            raise ValueError(f'expected float32 (or uint8) images, got {images.dtype}')
         images = np.ascontiguousarray(images)
         n = images.shape[0]
         if out is None:
             out = np.empty((n, self.n_joints_out, 3), dtype=np.float32)
         elif hasattr(out, 'numpy'):
             out = out.numpy()
-        _lib.check(self.lib.metro_infer_host(self._h, images.ctypes.data_as(C.c_void_p), n,
-                                             out.ctypes.data_as(C.c_void_p)))
+        fn = self.lib.metro_infer_host_u8 if images.dtype == np.uint8 else self.lib.metro_infer_host
+        _lib.check(fn(self._h, images.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def __call__(self, images):

@@ -167,3 +167,19 @@ def test_uint8_ingestion_matches_float_path():
     a = model.infer(u8)
     b = model.infer(u8.float() / 255.0)
     assert (a - b).abs().max().item() < 0.5
+
+
+def test_uint8_host_path_equals_device_path():
+    """metro_infer_host_u8 (uint8 crops over PCIe in slices) == metro_infer_u8 on the same crops, bit for bit, at a
+    batch that is not a multiple of the slice sizes."""
+    import torch
+    from metro_pose3d_b200.inference import MetroModel
+    n = 160
+    model = MetroModel('resnet_v2_50', 16, 'h36m', max_batch=n)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (n, 256, 256, 3), dtype=torch.uint8, generator=g)
+    host = model.infer_host(u8.numpy())
+    dev = model.infer(u8.cuda()).cpu().numpy()
+    assert np.array_equal(host, dev)
+    with pytest.raises(ValueError):
+        model.infer_host(u8.numpy().astype(np.int32))
