@@ -660,9 +660,12 @@ metro_status infer_host(metro_handle *h, const void *images_host_v, bool u8, int
     if (st != METRO_OK) return st;
     mark("stem", h->stream);
     const int done = lo + cnt;
-    // once no more than one tail slice is left to arrive, the deep blocks follow every stem slice, so that only
-    // one stem slice and one 64-crop tail remain after the last byte has crossed PCIe
-    if (done - tail_lo >= tail || n - tail_lo <= tail || done == n) {
+    // the deep blocks follow a stem slice once `tail` crops are ready -- except after the second-to-last slice:
+    // the GPU is the bottleneck of this call from the first slice on, nothing would fill the gap a split leaves,
+    // and one tail over the last two slices costs less than two (fixed ramp of ~45 launches per tail)
+    static const bool merge_last = std::getenv("METRO_HOST_NO_MERGE_LAST") == nullptr;
+    const bool second_to_last = merge_last && lo + chunk < n && lo + 2 * chunk >= n;
+    if (done == n || (done - tail_lo >= tail && !second_to_last)) {
       st = run_tail(h, done - tail_lo, tail_lo, stem_gemms, h->stage_pose, h->stream, nullptr);
       if (st != METRO_OK) return st;
       tail_lo = done;
