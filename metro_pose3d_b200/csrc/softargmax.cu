@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
     pix += p.lanes; ptr += stride;
   };
 
+  // this thread's slot of the output (joint after the export permutation, axis), fetched before the stream
+  const int out_jo = tid / 3, out_ax = tid - 3 * out_jo;
+  const int out_src = tid < p.n_out * 3 ? 3 * p.perm[out_jo] + out_ax : 0;
   // programmatic dependent launch: everything above overlaps the tail of the kernel that produces the head
   // tensor (the logits convolution); nothing before this line touches global memory
   const bool prof = p.prof != nullptr && tid == 0;
@@ -279,6 +282,8 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
         const float wgt = has ? pow2_neg_f32(k4[q] - km) : 0.f;    // a scale by 2^-d is exact short of underflow
         a4[q] = double(wgt * s4[q]); ax4[q] = double(wgt * x4[q]); ay4[q] = double(wgt * y4[q]);
       }
+      // (summing these four in fp32 instead saves ~170 cycles of the merge but doubles the error against the
+      // float64 oracle, 1.8e-4 -> 3.4e-4 mm: not taken)
       double a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
       double ax = (ax4[0] + ax4[1]) + (ax4[2] + ax4[3]);
       double ay = (ay4[0] + ay4[1]) + (ay4[2] + ay4[3]);
@@ -399,7 +404,9 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
     }
     __syncthreads();
   }
-  for (int i = tid; i < p.n_out * 3; i += blockDim.x) {
+  if (tid < p.n_out * 3)                  // n_out <= 64 and the CTA has >= 192 threads... or loops below
+    p.out[(size_t(img) * p.n_out) * 3 + tid] = float(s_c01[out_src] - s_c01[3 * p.root + out_ax]);
+  for (int i = tid + blockDim.x; i < p.n_out * 3; i += blockDim.x) {
     const int jo = i / 3, a = i - 3 * jo;
     p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
   }
