@@ -117,9 +117,11 @@ typedef struct metro_softargmax_desc {
   int32_t n_joints_out;
   const int32_t *permutation;
   int32_t head_dtype;         /* metro_dtype                                                       */
-  int32_t splits;             /* 0 = choose; >0 = CTAs per crop (tuning / tests)                   */
-  int32_t lanes;              /* 0 = choose; >0 = pixel lanes per CTA (tuning / tests)             */
-  int32_t word_bytes;         /* 0 = choose; 8 | 16 = bytes of one pixel a thread owns (tuning)    */
+  int32_t splits;             /* 0 = choose (shape-only rule); >0 = CTAs per crop (tuning / tests)  */
+  int32_t lanes;              /* 0 = choose; >0 = pixel lanes per CTA, rounded down to a power of
+                               * two <= 32 (tuning / tests)                                       */
+  int32_t word_bytes;         /* 0 = choose (16 for fp32 heads, 8 for fp16); 8 | 16 = bytes of one
+                               * pixel a thread owns (tuning)                                     */
 } metro_softargmax_desc;
 
 metro_status metro_softargmax_workspace_bytes(const metro_softargmax_desc *d, int32_t n,

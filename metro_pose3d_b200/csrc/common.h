@@ -34,6 +34,7 @@ struct SoftargmaxLaunch {
   double mul_x, mul_y, mul_z;  // mm per unit of (Sx/S), (Sy/S), (Sz/S)
   int splits, ipx;         // work items per crop and pixels per item (shape-only rule)
   int lanes, slots, vec;   // CTA = slots channel words x lanes pixel lanes; vec channels per word
+  int cluster;             // 1 = the splits of a crop form a thread-block cluster (DSMEM merge, no workspace traffic)
   int tpj;                 // threads per joint in the merge (power of two <= 32)
   long long *prof;         // debug (METRO_SAM_PROF): 8 clock64 stamps per CTA, or null
   int head_f16;

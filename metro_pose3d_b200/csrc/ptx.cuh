@@ -237,6 +237,10 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// 64-bit store into the shared memory of another CTA of the cluster (address from mapa)
+__device__ __forceinline__ void st_cluster_f64(uint32_t cluster_addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+}
 // shared::cluster address of the same shared-memory variable in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
   float *s_k = reinterpret_cast<float *>(smem_raw);                              // [lanes][C] exponent
   float *s_s = s_k + LC, *s_x = s_s + LC, *s_y = s_x + LC;                       // [lanes][C] sums
   double *s_c01 = reinterpret_cast<double *>(s_y + LC);                          // [J][3] coordinates in mm
+  double *s_part = s_c01 + 3 * J;                                                // [splits][J][5], cluster launches
   __shared__ int s_is_last;
 
   const int item = blockIdx.x;
@@ -256,6 +257,18 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
   }
   __syncthreads();
   if (prof) stamp[3] = clock64();
+  // a split crop's per-joint record goes to the first CTA of its cluster through distributed shared memory, or
+  // -- when the launch has no clusters (split counts that are not 2, 4 or 8) -- to the global workspace
+  auto emit_partial = [&](int j, double km, double a, double ax, double ay, double az) {
+    if (p.cluster) {
+      const uint32_t dst = ptx::mapa(ptx::smem_u32(s_part + (split * J + j) * 5), 0);
+      ptx::st_cluster_f64(dst, km); ptx::st_cluster_f64(dst + 8, a); ptx::st_cluster_f64(dst + 16, ax);
+      ptx::st_cluster_f64(dst + 24, ay); ptx::st_cluster_f64(dst + 32, az);
+    } else {
+      double *rec = p.partials + ((size_t(img) * p.splits + split) * J + j) * 5;
+      rec[0] = km; rec[1] = a; rec[2] = ax; rec[3] = ay; rec[4] = az;
+    }
+  };
   // lanes x depth -> joint in one stage: `tpj` adjacent threads per joint (a power of two, all warps busy), each
   // takes its share of the joint's D x lanes records -- exact power-of-two weights, fp64 sums -- and a butterfly
   // over the tpj threads finishes the sum
@@ -294,8 +307,7 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
       }
       if (has && i == 0) {
         if (p.splits > 1) {
-          double *rec = p.partials + ((size_t(img) * p.splits + split) * J + j) * 5;
-          rec[0] = double(km); rec[1] = a; rec[2] = ax; rec[3] = ay; rec[4] = az;
+          emit_partial(j, double(km), a, ax, ay, az);
         } else {
           const double inv = recip(a);
           s_c01[3 * j] = ax * inv * p.mul_x;
@@ -339,8 +351,7 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
       }
       if (has && i == 0) {
         if (p.splits > 1) {
-          double *rec = p.partials + ((size_t(img) * p.splits + split) * J + j) * 5;
-          rec[0] = double(km); rec[1] = a; rec[2] = ax; rec[3] = ay; rec[4] = az;
+          emit_partial(j, double(km), a, ax, ay, az);
         } else {
           // expectation of linspace(0,1,n) along each axis == E[index]/(n-1); mul_* carry 1/(n-1) and mm
           const double inv = recip(a);
@@ -353,7 +364,27 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
   }
   __syncthreads();
   if (prof) stamp[4] = clock64();
-  if (p.splits > 1) {
+  if (p.splits > 1 && p.cluster) {
+    // the `splits` CTAs of a crop form one thread-block cluster: records were stored into CTA 0's shared memory
+    // above; one cluster barrier (release / acquire) later CTA 0 merges them, the others are done
+    ptx::cluster_sync();
+    if (split != 0) return;
+    if (tid < J) {
+      double gk = s_part[tid * 5];
+      for (int sp = 1; sp < p.splits; ++sp) gk = fmax(gk, s_part[(sp * J + tid) * 5]);
+      double TS = 0.0, TX = 0.0, TY = 0.0, TZ = 0.0;
+      for (int sp = 0; sp < p.splits; ++sp) {
+        const double *rec = s_part + (sp * J + tid) * 5;
+        const double wgt = pow2_neg(float(rec[0] - gk));
+        TS += wgt * rec[1]; TX += wgt * rec[2]; TY += wgt * rec[3]; TZ += wgt * rec[4];
+      }
+      const double inv = recip(TS);
+      s_c01[3 * tid] = TX * inv * p.mul_x;
+      s_c01[3 * tid + 1] = TY * inv * p.mul_y;
+      s_c01[3 * tid + 2] = TZ * inv * p.mul_z;
+    }
+    __syncthreads();
+  } else if (p.splits > 1) {
     // the last CTA of the crop merges the per-split records.  bar.sync above orders the J writers before
     // thread 0, whose gpu-scope fence is cumulative over what it has observed.
     if (tid == 0) {
@@ -414,7 +445,8 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
 }
 
 size_t smem_bytes(const SoftargmaxLaunch &L) {
-  return size_t(4) * L.lanes * L.C * sizeof(float) + size_t(3) * L.J * sizeof(double) + 16;
+  return size_t(4) * L.lanes * L.C * sizeof(float) + size_t(3) * L.J * sizeof(double) +
+         (L.cluster ? size_t(L.splits) * L.J * 5 * sizeof(double) : 0) + 16;
 }
 
 template <int VEC, bool F16, int CH, int MAXT, int MINB>
@@ -428,10 +460,22 @@ metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
   const dim3 grid(unsigned(L.n) * unsigned(L.splits)), block(unsigned((L.slots * L.lanes + 31) & ~31));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = sm; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  static const bool no_pdl = std::getenv("METRO_NO_PDL") != nullptr;   // A/B switch shared with the conv launches
+  if (!no_pdl) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  if (L.cluster) {                       // the CTAs of one crop are consecutive in the grid
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = unsigned(L.splits);
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr; cfg.numAttrs = unsigned(n_attr);
   static const bool want_prof = std::getenv("METRO_SAM_PROF") != nullptr;
   if (!want_prof) {
     METRO_CUDA(cudaLaunchKernelEx(&cfg, softargmax_kernel<VEC, F16, CH, MAXT, MINB>, L));
@@ -515,12 +559,14 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
     L.tpj = 32;
     while (L.tpj > 1 && L.J * L.tpj > threads) L.tpj /= 2;
   }
-  // work items: one per crop, or -- for large heatmaps -- up to four row-major pixel ranges of >= 256 pixels
-  // (a CTA lives ~3 us beyond its streaming time, so items must be long; four per crop keep a 64-crop shard
-  // of 32x32 heatmaps at one full wave of CTAs).  The number of ranges depends on the heatmap shape ONLY, so
-  // a crop's result is bit-identical whatever batch or GPU shard it is part of (merged by the last CTA of the
-  // crop to finish)
-  int item_px = kItemPixels, max_splits = 4;
+  // work items: one per crop, or -- for heatmaps above 256 pixels -- row-major pixel ranges: four per crop up to
+  // 32x32, two above (a CTA lives ~2500 cycles beyond its streaming time, so items must be long and one wave of
+  // CTAs is the target: 64 crops x 4 at stride 8, 128 crops x 2 at stride 4 are the per-GPU shards of the
+  // reference configurations; measured 10.7 us against 13.1 with two ranges at 32x32, 54.9 against 57.9 with
+  // four at 64x64).  The number of ranges depends on the heatmap shape ONLY, so a crop's result is bit-identical
+  // whatever batch or GPU shard it is part of.  The CTAs of a crop form a thread-block cluster and merge through
+  // distributed shared memory.
+  int item_px = kItemPixels, max_splits = P > 1024 ? 2 : 4;
   if (const char *e = getenv("METRO_SAM_ITEM_PX")) item_px = atoi(e) > 0 ? atoi(e) : item_px;
   if (const char *e = getenv("METRO_SAM_MAX_SPLITS")) max_splits = atoi(e) > 0 ? atoi(e) : max_splits;
   int splits = d.splits > 0 ? d.splits : (P + item_px - 1) / item_px;
@@ -529,6 +575,8 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   if (splits > P) splits = P;
   L.ipx = (P + splits - 1) / splits;
   L.splits = (P + L.ipx - 1) / L.ipx;              // no empty item
+  // 2, 4 or 8 CTAs per crop run as one thread-block cluster and merge through distributed shared memory
+  L.cluster = (L.splits == 2 || L.splits == 4 || L.splits == 8) && !getenv("METRO_SAM_NO_CLUSTER") ? 1 : 0;
   if (smem_bytes(L) > 100 * 1024) return fail(METRO_ERR_VALUE, "softargmax: shared memory budget exceeded");
   return METRO_OK;
 }
