@@ -12,10 +12,11 @@
 //   out[n,jo,:] = (E_j[w]/(W-1), E_j[h]/(H-1), E_j[d]/(D-1)) - same for the root, times mm scales.
 //
 // Layout of work: the head tensor of a crop is a contiguous run of 16-byte words (8-byte words for an fp16
-// head), `slots` words per pixel.  A work item is one crop or -- for heatmaps above 256 pixels -- one of up to
-// four row-major pixel ranges (a rule that depends on the heatmap shape only), one CTA per item, two CTAs
-// resident per SM.  The CTA has slots x lanes threads (272-304 for the reference shapes); thread t owns channel
-// slot t % slots and walks pixels (t / slots), + lanes, ...: consecutive threads read consecutive words, so
+// head), `slots` words per pixel.  A work item is one crop or -- for heatmaps above 256 pixels -- one of four
+// (two above 32x32) row-major pixel ranges, a rule that depends on the heatmap shape only; one CTA per item,
+// two CTAs resident per SM; the CTAs of a split crop form a thread-block cluster.  The CTA has slots x lanes
+// threads (272-304 for the reference shapes); thread t owns channel slot t % slots and walks pixels
+// (t / slots), + lanes, ...: consecutive threads read consecutive words, so
 // every warp request is 512 contiguous bytes.  The stream goes global -> registers in chunks of 8 words per
 // thread; a register word is reloaded with the next chunk's data after its last use, so the loads of chunk
 // k+1 are in flight underneath the arithmetic of chunk k.  No shared-memory staging, no block-wide
@@ -32,8 +33,10 @@
 // merge (lanes x depth -> joint -> CTA splits) is fp64 with weights that are exact powers of two applied
 // in fp32 (an exact scaling): no transcendental and no rounding in any merge weight.  The only fp32 roundings are ex2.approx per
 // element and the short per-thread sums, which keeps the result within 1e-3 mm of the float64 oracle.
-// When a crop is split over several CTAs the last CTA to finish (ticket counter) merges the per-split
-// records; the workspace counters are left zeroed for the next launch.
+// When a crop is split over 2, 4 or 8 CTAs they are one cluster: every CTA stores its per-joint records into
+// the first CTA's shared memory (st.shared::cluster), one cluster barrier later that CTA merges them.  Other
+// split counts (tests, tuning) fall back to a global workspace and a ticket counter -- the last CTA to finish
+// merges -- which is left zeroed for the next launch.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
   // tensor (the logits convolution); nothing before this line touches global memory
   const bool prof = p.prof != nullptr && tid == 0;
   long long *stamp = p.prof + size_t(blockIdx.x) * 8;
-  if (prof) stamp[0] = clock64();
+  if (prof) { stamp[0] = clock64(); stamp[6] = (long long)ptx::globaltimer(); }
   ptx::griddep_wait();
   ptx::griddep_launch_dependents();
   if (prof) stamp[1] = clock64();
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
     const int jo = i / 3, a = i - 3 * jo;
     p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
   }
-  if (prof) stamp[5] = clock64();
+  if (prof) { stamp[5] = clock64(); stamp[7] = (long long)ptx::globaltimer(); }
 }
 
 size_t smem_bytes(const SoftargmaxLaunch &L) {
@@ -497,6 +500,16 @@ metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
       const double d = double(hst[c * 8 + i + 1] - hst[c * 8 + i]);
       sum[i] += d; if (d > mx[i]) mx[i] = d;
     }
+  long long t_first = 0, t_last = 0, t_first_end = 0;
+  for (size_t c = 0; c < n_ctas; ++c) {
+    const long long b = hst[c * 8 + 6], e = hst[c * 8 + 7];
+    if (b == 0 || e == 0) continue;                      // a CTA that left early (split crop, not the finisher)
+    if (t_first == 0 || b < t_first) t_first = b;
+    if (e > t_last) t_last = e;
+    if (t_first_end == 0 || e < t_first_end) t_first_end = e;
+  }
+  std::fprintf(stderr, "[metro sam prof] first CTA start -> last CTA end %.2f us (first CTA end after %.2f us)\n",
+               double(t_last - t_first) * 1e-3, double(t_first_end - t_first) * 1e-3);
   std::fprintf(stderr, "[metro sam prof] %zu CTAs x %u threads, cycles avg/max: wait %.0f/%.0f stream %.0f/%.0f records %.0f/%.0f merge %.0f/%.0f out %.0f/%.0f\n",
                n_ctas, block.x, sum[0] / n_ctas, mx[0], sum[1] / n_ctas, mx[1], sum[2] / n_ctas, mx[2], sum[3] / n_ctas, mx[3],
                sum[4] / n_ctas, mx[4]);
