@@ -132,6 +132,15 @@ metro_status metro_softargmax_workspace_bytes(const metro_softargmax_desc *d, in
 metro_status metro_softargmax(const metro_softargmax_desc *d, const void *head_dev, int32_t n,
                               float *poses_dev, void *workspace_dev, void *stream);
 
+/* ---- post-path: back into the original camera frame.  Replaces to_orig_cam
+ *      (volumetric.py:277-282): out[b,c,:] = R[b] @ poses[b,c',:], c' = c where det(R[b]) > 0, else
+ *      mirror_mapping[c] (the crop was flipped, data_loading.py:80-83; JointInfo.mirror_mapping,
+ *      datasets.py:76-79).  poses_dev / out_dev: device float32 [n, n_joints, 3] (must not alias);
+ *      rot_dev: device float32 [n, 3, 3] row-major; mirror_mapping: HOST int32 [n_joints]. ----------- */
+metro_status metro_to_orig_cam(const float *poses_dev, const float *rot_dev,
+                               const int32_t *mirror_mapping, int32_t n, int32_t n_joints,
+                               float *out_dev, void *stream);
+
 /* ---- single fused convolution (operator-level entry point used by the parity tests) ----------- */
 typedef struct metro_conv_desc {
   int32_t n, in_side, cin, cout, k, stride, rate, pad_lo;  /* conv2d_same geometry (resnet_utils.py:82-135) */

@@ -43,4 +43,8 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
 size_t softargmax_workspace_bytes(const SoftargmaxLaunch &L);
 metro_status softargmax_launch(const SoftargmaxLaunch &L, cudaStream_t stream);
 
+// ---- post-path transforms ---------------------------------------------------------------------------
+metro_status to_orig_cam_launch(const float *poses, const float *rot, const int32_t *mirror, int n, int j, float *out,
+                                cudaStream_t stream);
+
 }  // namespace metro

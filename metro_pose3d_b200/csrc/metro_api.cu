@@ -689,6 +689,20 @@ metro_status infer_host(metro_handle *h, const void *images_host_v, bool u8, int
 }
 }  // namespace
 
+metro_status metro_to_orig_cam(const float *poses_dev, const float *rot_dev, const int32_t *mirror_mapping, int32_t n,
+                               int32_t n_joints, float *out_dev, void *stream) {
+  if (n < 0) return fail(METRO_ERR_VALUE, "to_orig_cam: negative batch");
+  if (n_joints <= 0 || n_joints > kMaxJointsOut) return fail(METRO_ERR_VALUE, "to_orig_cam: n_joints must be in [1, %d]", kMaxJointsOut);
+  if (!mirror_mapping) return fail(METRO_ERR_VALUE, "to_orig_cam: null mirror mapping");
+  for (int i = 0; i < n_joints; ++i)
+    if (mirror_mapping[i] < 0 || mirror_mapping[i] >= n_joints)
+      return fail(METRO_ERR_VALUE, "to_orig_cam: mirror_mapping[%d]=%d out of range [0,%d)", i, mirror_mapping[i], n_joints);
+  if (n == 0) return METRO_OK;
+  if (!poses_dev || !rot_dev || !out_dev) return fail(METRO_ERR_VALUE, "to_orig_cam: null device buffer");
+  if (poses_dev == out_dev) return fail(METRO_ERR_VALUE, "to_orig_cam: the output must not alias the input (joints are gathered)");
+  return to_orig_cam_launch(poses_dev, rot_dev, mirror_mapping, n, n_joints, out_dev, static_cast<cudaStream_t>(stream));
+}
+
 metro_status metro_softargmax_workspace_bytes(const metro_softargmax_desc *d, int32_t n, uint64_t *bytes) {
   if (!d || !bytes) return fail(METRO_ERR_VALUE, "null argument");
   SoftargmaxLaunch L;

@@ -268,3 +268,24 @@ def conv2d(x, w_hwio: np.ndarray, scale: np.ndarray, shift: np.ndarray, stride: 
                                 p(scale), p(shift), None if res is None else res.data_ptr(), y.data_ptr(),
                                 p(scale2), p(shift2), None if y2 is None else y2.data_ptr(), x.device.index or 0, stream))
     return (y, y2) if y2 is not None else y
+
+
+def to_orig_cam(poses, rot_to_orig_cam, mirror_mapping: Sequence[int]):
+    """``to_orig_cam`` of the reference's evaluation graph (src/model/volumetric.py:277-282) on device tensors:
+    poses float32 ``[N, J, 3]``, rotations float32 ``[N, 3, 3]``; ``mirror_mapping`` as
+    ``JointInfo.mirror_mapping`` (datasets.py:76-79).  Returns a new ``[N, J, 3]`` tensor."""
+    torch = _torch()
+    if poses.dim() != 3 or poses.shape[2] != 3 or poses.dtype != torch.float32 or not poses.is_cuda:
+        raise ValueError('expected a CUDA float32 [N, J, 3] tensor of poses')
+    n, j = poses.shape[0], poses.shape[1]
+    if tuple(rot_to_orig_cam.shape) != (n, 3, 3) or rot_to_orig_cam.dtype != torch.float32 or not rot_to_orig_cam.is_cuda:
+        raise ValueError(f'expected a CUDA float32 [{n}, 3, 3] tensor of rotations')
+    if len(mirror_mapping) != j:
+        raise ValueError(f'mirror_mapping has {len(mirror_mapping)} entries for {j} joints')
+    lib = _lib.load()
+    poses, rot = poses.contiguous(), rot_to_orig_cam.contiguous()
+    out = torch.empty_like(poses)
+    mm = (C.c_int32 * j)(*[int(v) for v in mirror_mapping])
+    stream = torch.cuda.current_stream(poses.device).cuda_stream
+    _lib.check(lib.metro_to_orig_cam(poses.data_ptr(), rot.data_ptr(), C.cast(mm, C.c_void_p), n, j, out.data_ptr(), stream))
+    return out

@@ -36,6 +36,20 @@ class JointInfo:
     def n_joints(self) -> int:
         return len(self.names)
 
+    @property
+    def mirror_mapping(self) -> List[int]:
+        """Index of the joint on the opposite body side (datasets.py:76-79,95-102): an 'l' / 'r' first letter is
+        swapped, every other name maps to itself."""
+        ids = {n: i for i, n in enumerate(self.names)}
+
+        def other(name):
+            if name.startswith('l'):
+                return 'r' + name[1:]
+            if name.startswith('r'):
+                return 'l' + name[1:]
+            return name
+        return [ids[other(n)] for n in self.names]
+
     def permute_joints(self, permutation: Sequence[int]) -> 'JointInfo':
         """datasets.py:105-109.  As in the reference, edges whose endpoints are not selected by
         ``permutation`` cannot be expressed; the reference would raise on them, so do we."""

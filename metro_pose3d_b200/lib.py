@@ -19,7 +19,7 @@ METRO_F32, METRO_F16 = 0, 1
 
 EXPORTS = [
     'metro_last_error', 'metro_version', 'metro_blob_floats', 'metro_plan_describe', 'metro_create',
-    'metro_destroy', 'metro_workspace_bytes', 'metro_infer', 'metro_infer_host', 'metro_infer_u8', 'metro_infer_host_u8',
+    'metro_destroy', 'metro_workspace_bytes', 'metro_infer', 'metro_infer_host', 'metro_infer_u8', 'metro_infer_host_u8', 'metro_to_orig_cam',
     'metro_softargmax_workspace_bytes', 'metro_softargmax', 'metro_conv2d', 'metro_debug_read',
     'metro_profile', 'metro_launch_count',
 ]
@@ -90,6 +90,7 @@ def load() -> C.CDLL:
     lib.metro_infer_u8.argtypes = [vp, vp, i32, vp, vp]
     lib.metro_infer_host.argtypes = [vp, vp, i32, vp]
     lib.metro_infer_host_u8.argtypes = [vp, vp, i32, vp]
+    lib.metro_to_orig_cam.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.metro_softargmax_workspace_bytes.argtypes = [C.POINTER(SoftargmaxDesc), i32, C.POINTER(u64)]
     lib.metro_softargmax.argtypes = [C.POINTER(SoftargmaxDesc), vp, i32, vp, vp, vp]
     lib.metro_conv2d.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]

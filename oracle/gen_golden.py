@@ -158,7 +158,29 @@ def run_decode(tf, flags, tfu, head_nhwc, joint_info, permutation, stride, proc_
     return out.value, coords3d.value
 
 
-def main():
+def run_to_orig_cam(tf, poses, rot, joint_info):
+    """volumetric.to_orig_cam (src/model/volumetric.py:277-282) on given poses / rotations."""
+    import model.volumetric as V
+    return V.to_orig_cam(tf.convert_to_tensor(poses), tf.convert_to_tensor(rot), joint_info).value
+
+
+def synth_rotations(n, seed):
+    """n 3x3 matrices: proper rotations, every second one composed with a horizontal flip (det < 0), which is
+    what `rot_to_orig_cam = ex.camera.R @ cam.R.T` holds after cam.horizontal_flip() (data_loading.py:80-83,110)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        q, r = np.linalg.qr(rng.randn(3, 3))
+        q = q * np.sign(np.diag(r))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        if i % 2 == 1:
+            q = q @ np.diag([-1.0, 1.0, 1.0])
+        out.append(q)
+    return np.stack(out)
+
+
+def main(only=None):
     from metro_pose3d_b200.spec import NetSpec
     from metro_pose3d_b200.weights import synth_head, synth_images, synth_weights
     tf, flags, tfu = _install_reference()
@@ -173,11 +195,27 @@ def main():
         tables[f'{ds}_model_names'] = np.array(ji.names)
         tables[f'{ds}_model_edges'] = np.array(ji.stick_figure_edges, dtype=np.int64)
         tables[f'{ds}_permutation'] = np.array(perm, dtype=np.int64)
+        tables[f'{ds}_model_mirror'] = np.array(ji.mirror_mapping, dtype=np.int64)
         if ds == 'h36m':       # permute_joints needs every edge endpoint selected (true for h36m)
             pj = ji.permute_joints(perm)
             tables[f'{ds}_export_names'] = np.array(pj.names)
             tables[f'{ds}_export_edges'] = np.array(pj.stick_figure_edges, dtype=np.int64)
+            tables[f'{ds}_export_mirror'] = np.array(pj.mirror_mapping, dtype=np.int64)
     np.savez_compressed(os.path.join(out_dir, 'joints.npz'), **tables)
+
+    # ---- post-path: to_orig_cam on seeded poses and rotations -----------------------
+    post = {}
+    for ds in ('h36m', 'merged'):
+        ji = reference_joint_info(ds)
+        n = 6
+        rng = np.random.RandomState(7 + ji.n_joints)
+        poses = rng.randn(n, ji.n_joints, 3) * 400.0
+        rot = synth_rotations(n, 11 + ji.n_joints)
+        post[f'{ds}_orig_cam'] = run_to_orig_cam(tf, poses, rot, ji)
+        post[f'{ds}_meta'] = np.array([n, ji.n_joints, 7 + ji.n_joints, 11 + ji.n_joints])
+    np.savez_compressed(os.path.join(out_dir, 'post.npz'), **post)
+    if only == 'post':
+        return
 
     # ---- decode only: every stride / joint-set / layout the configs use ------------------------------
     dec = {}
@@ -237,4 +275,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)     # `gen_golden.py post`: joint tables and post-path vectors only

@@ -290,3 +290,15 @@ def conv2d_naive(x_nhwc, w_hwio, stride, rate, pad_lo, pad_hi):
                 for kw in range(k):
                     out[:, i, j, :] += xp[:, i * stride + kh * rate, j * stride + kw * rate, :] @ w[kh, kw]
     return out
+
+
+def to_orig_cam_ref(poses: np.ndarray, rot_to_orig_cam: np.ndarray, mirror_mapping: Sequence[int]) -> np.ndarray:
+    """Post-path step of the reference's evaluation graph (src/model/volumetric.py:277-282):
+    x' = einsum('Bij,BCj->BCi', R, x) (matmul_joint_coords, :221-222); where det(R) > 0 keep x', otherwise --
+    the crop was flipped horizontally, data_loading.py:80-83 -- take x' with left and right joints swapped
+    (gather by JointInfo.mirror_mapping, datasets.py:76-79).  float64."""
+    x = np.asarray(poses, np.float64)
+    r = np.asarray(rot_to_orig_cam, np.float64)
+    y = np.einsum('bij,bcj->bci', r, x)
+    keep = np.linalg.det(r) > 0
+    return np.where(keep[:, None, None], y, y[:, list(mirror_mapping)])

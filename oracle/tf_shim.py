@@ -110,6 +110,7 @@ class Tensor:
     def __rmul__(self, o): return self._bin(o, np.multiply, True)
     def __truediv__(self, o): return self._bin(o, np.divide)
     def __neg__(self): return Tensor(-self.value, self.dtype)
+    def __gt__(self, o): return Tensor(np.greater(self.value, _v(o)), bool_)
 
     def __getitem__(self, idx):
         if isinstance(idx, list):
@@ -291,6 +292,23 @@ def expand_dims(x, axis, name=None):
 
 def gather(params, indices, axis=0, name=None):
     return Tensor(np.take(_v(params), np.asarray(indices), axis=axis), params.dtype, name)
+
+
+def einsum(equation, *inputs, name=None):
+    return Tensor(np.einsum(equation, *[_v(x) for x in inputs]))
+
+
+def where(condition, x=None, y=None, name=None):
+    """TF 1.x semantics for a rank-1 condition: it selects whole rows (first axis) of x / y."""
+    c = np.asarray(_v(condition))
+    xv, yv = _v(x), _v(y)
+    if c.ndim == 1 and xv.ndim > 1:
+        c = c.reshape((-1,) + (1,) * (xv.ndim - 1))
+    return Tensor(np.where(c, xv, yv))
+
+
+def det(x, name=None):
+    return Tensor(np.linalg.det(_v(x)))
 
 
 def ones_like(x, dtype=None, name=None):
@@ -492,7 +510,8 @@ def install():
         as_dtype=as_dtype, convert_to_tensor=convert_to_tensor, cast=cast, identity=identity, reshape=reshape,
         transpose=transpose, reduce_max=reduce_max, reduce_sum=reduce_sum, reduce_mean=reduce_mean, exp=exp,
         linspace=linspace, squeeze=squeeze, stack=stack, concat=concat, expand_dims=expand_dims, gather=gather,
-        ones_like=ones_like, zeros_like=zeros_like, pad=pad, variable_scope=variable_scope, name_scope=name_scope,
+        ones_like=ones_like, zeros_like=zeros_like, pad=pad, einsum=einsum, where=where,
+        linalg=_module('tensorflow.linalg', det=det), variable_scope=variable_scope, name_scope=name_scope,
         nn=nn, contrib=contrib, python=python, shim=this)
 
     class AttrDict(dict):
