@@ -1,5 +1,7 @@
+"""Per-CTA phase timers of the soft-argmax (run with METRO_SAM_PROF=1): stream / records / merge / output cycles and
+the first-CTA-start to last-CTA-end span, for the BASELINE shapes and two split settings."""
 import os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from metro_pose3d_b200.inference import SoftArgmax
 from metro_pose3d_b200.weights import synth_head
