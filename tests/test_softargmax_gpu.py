@@ -49,9 +49,11 @@ def test_parity_fp16_head(side, stride, j, ds, n):
     assert np.abs(got - ref).max() < TOL_MM
 
 
-@pytest.mark.parametrize('splits,lanes', [(1, 11), (2, 8), (5, 4), (16, 1), (3, 0)])
+@pytest.mark.parametrize('splits,lanes', [(1, 11), (2, 8), (5, 4), (16, 1), (3, 0), (8, 8), (4, 16)])
 def test_cross_cta_merge_paths(splits, lanes):
-    """Different (splits, lanes) exercise the single-CTA path, the ticketed multi-CTA merge and ragged tails."""
+    """Different (splits, lanes) exercise the single-CTA path, the cluster merge through distributed shared memory
+    (2, 4, 8 CTAs per crop), the ticketed multi-CTA merge of the other split counts, the wide-CTA variant and ragged
+    tails."""
     perm = export_permutation('h36m')
     x = synth_head(6, 16, 17, seed=11, sigma=4.0)
     ref = decode_ref(x, 17, 16, perm)
