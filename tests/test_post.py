@@ -84,3 +84,22 @@ def test_cuda_to_orig_cam_argument_errors():
         to_orig_cam(x, r, [17] * 17)
     with pytest.raises(ValueError):
         to_orig_cam(x, r[:1], list(range(17)))
+
+
+def test_round_trip_property():
+    """Size-independent property: rotating into the original camera and back with the transposed matrix returns
+    the skeleton, flipped crops included (the left/right swap is an involution and commutes with the rotation)."""
+    rng = np.random.RandomState(3)
+    mm = model_joint_info('merged').mirror_mapping
+    x = rng.randn(64, len(mm), 3) * 300.0
+    rots = []
+    for i in range(64):
+        q, r = np.linalg.qr(rng.randn(3, 3))
+        q = q * np.sign(np.diag(r))
+        if (np.linalg.det(q) < 0) != (i % 3 == 0):        # every third matrix is a reflection
+            q[:, 0] = -q[:, 0]
+        rots.append(q)
+    rot = np.stack(rots)
+    y = to_orig_cam_ref(x, rot, mm)
+    back = to_orig_cam_ref(y, np.transpose(rot, (0, 2, 1)), mm)
+    assert np.abs(back - x).max() < 1e-9
