@@ -10,7 +10,10 @@ This module parses that file with a ~100-line protobuf wire-format reader (field
 tensorflow/core/framework/{graph,node_def,attr_value,tensor,tensor_shape,types}.proto, TF 1.13) and
 recovers, by walking the graph rather than trusting constant names (fold_constants renames them):
 
-* per ``Conv2D`` scope: the HWIO filter, the ``BiasAdd`` vector, the four ``FusedBatchNorm`` vectors;
+* per ``Conv2D`` scope: the HWIO filter, the ``BiasAdd`` vector, the four ``FusedBatchNorm`` vectors -- or, for a
+  batch norm built from primitive ops and folded by ``fold_constants`` / ``fold_batch_norms``, the remaining
+  ``batchnorm/mul_1`` scale and ``batchnorm/add_1`` offset (the scale already inside the filter behind a
+  convolution), re-expressed as gamma / beta / mean 0 / variance 1 - eps;
 * the architecture (scope prefix), the head width (``depth * n_joints``), the stride (product of the conv
   strides), the export permutation, ``joint_names`` and ``joint_edges``.
 
@@ -28,7 +31,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from .spec import NetSpec
+from .spec import BN_EPS, NetSpec
 from .weights import blob_order
 
 # tensorflow/core/framework/types.proto
@@ -229,6 +232,7 @@ def import_frozen_graph(data: bytes, depth: int = 8) -> FrozenModel:
     m = FrozenModel()
     m.depth = depth
     found: Dict[str, np.ndarray] = {}
+    decomposed: Dict[str, Dict[str, np.ndarray]] = {}     # BN scope -> {'scale', 'offset'} of a non-fused batch norm
     stride_product = 1
     for node in nodes.values():
         if '/resnet_v2_' not in node.name:
@@ -259,12 +263,32 @@ def import_frozen_graph(data: bytes, depth: int = 8) -> FrozenModel:
                 if v is None:
                     raise ValueError(f'{node.name}: {leaf} is not a constant')
                 found[f'{scope}/{leaf}'] = np.asarray(v, np.float32)
+        elif node.op in ('Mul', 'Add', 'AddV2') and '/batchnorm/' in local:
+            # a batch norm built from primitive ops, after fold_constants (+ fold_batch_norms behind a convolution):
+            # `<scope>/batchnorm/mul_1` = x * scale, `<scope>/batchnorm/add_1` = ... + offset
+            bn_scope, leaf = local.split('/batchnorm/', 1)
+            consts = [c for c in (_const_of(nodes, r) for r in node.inputs[:2]) if c is not None]
+            if leaf == 'mul_1' and node.op == 'Mul' and len(consts) == 1:
+                decomposed.setdefault(bn_scope, {})['scale'] = np.asarray(consts[0], np.float32).reshape(-1)
+            elif leaf == 'add_1' and node.op != 'Mul' and len(consts) == 1:
+                decomposed.setdefault(bn_scope, {})['offset'] = np.asarray(consts[0], np.float32).reshape(-1)
         elif node.op in ('MaxPool',):
             s = node.attr.get('strides') or [1]
             if 'pool1' in node.name:
                 stride_product *= max(s)
     if not m.arch:
         raise ValueError('no resnet_v2_50 / resnet_v2_101 scope in the graph')
+    # A decomposed batch norm y = x * scale + offset (scale already inside the filter when it followed a
+    # convolution) is expressed in the blob's terms as gamma = scale, beta = offset, mean = 0 and a variance that
+    # makes gamma / sqrt(variance + eps) == gamma: metro_create folds the four vectors back into scale / shift.
+    for bn_scope, so in decomposed.items():
+        if f'{bn_scope}/gamma' in found or 'offset' not in so:
+            continue
+        off = so['offset']
+        found[f'{bn_scope}/gamma'] = so.get('scale', np.ones_like(off))
+        found[f'{bn_scope}/beta'] = off
+        found[f'{bn_scope}/moving_mean'] = np.zeros_like(off)
+        found[f'{bn_scope}/moving_variance'] = np.full_like(off, 1.0 - BN_EPS)
     if 'logits/weights' not in found:
         raise ValueError('no logits convolution in the graph')
     head = found['logits/weights'].shape[3]

@@ -67,10 +67,17 @@ def node(name, op, inputs=(), **attrs) -> bytes:
     return _ld(1, body)
 
 
-def frozen_graph(spec, weights, permutation, joint_names, joint_edges, half=False, prefix='MainPart'):
+def frozen_graph(spec, weights, permutation, joint_names, joint_edges, half=False, prefix='MainPart', bn_form='fused',
+                 eps=1e-5):
     """GraphDef bytes.  Constants get fold_constants-style names (not the variable names) and reach their
     consumers through Identity nodes; fp16 graphs store half constants, alternating the two TensorProto
-    encodings (tensor_content / typed value list)."""
+    encodings (tensor_content / typed value list).
+
+    bn_form='fused'  : FusedBatchNorm nodes with their four constants (what slim's fused batch norm exports).
+    bn_form='folded' : what fold_constants + fold_batch_norms leave of a batch norm built from primitive ops
+                       (tf.nn.batch_normalization): after a convolution the scale is folded into the filter and
+                       only `<scope>/batchnorm/add_1` (Add with a constant) remains; a batch norm that does not
+                       follow a convolution (preact, postnorm) is `<scope>/batchnorm/mul_1` + `.../add_1`."""
     out = [node('input', 'Placeholder')]
     root = f'{prefix}/{spec.arch}'
     counter = [0]
@@ -84,19 +91,38 @@ def frozen_graph(spec, weights, permutation, joint_names, joint_edges, half=Fals
         out.append(node(name + '/read', 'Identity', [name]))
         return name + '/read'
 
+    def scale_offset(scope):
+        g, b, m, v = (np.asarray(weights[f'{scope}/{leaf}'], np.float64)
+                      for leaf in ('gamma', 'beta', 'moving_mean', 'moving_variance'))
+        sc = g / np.sqrt(v + eps)
+        return sc, b - m * sc
+
     def conv(c, scope, src):
         s = c.stride
-        out.append(node(f'{root}/{scope}/Conv2D', 'Conv2D', [src, const(weights[f'{scope}/weights'])],
+        w = weights[f'{scope}/weights']
+        fold = bn_form == 'folded' and c.has_bn
+        if fold:
+            sc, off = scale_offset(f'{scope}/BatchNorm')
+            w = np.asarray(w, np.float64) * sc                       # HWIO: the scale runs along the output channels
+        out.append(node(f'{root}/{scope}/Conv2D', 'Conv2D', [src, const(w)],
                         strides=attr_ints([1, 1, s, s]), data_format=attr_str('NCHW')))
         last = f'{root}/{scope}/Conv2D'
         if c.has_bias:
             out.append(node(f'{root}/{scope}/BiasAdd', 'BiasAdd', [last, const(weights[f'{scope}/biases'])]))
             last = f'{root}/{scope}/BiasAdd'
-        if c.has_bn:
+        if fold:
+            out.append(node(f'{root}/{scope}/BatchNorm/batchnorm/add_1', 'Add', [last, const(off)]))
+            last = f'{root}/{scope}/BatchNorm/batchnorm/add_1'
+        elif c.has_bn:
             last = bn(f'{scope}/BatchNorm', last)
         return last
 
     def bn(scope, src):
+        if bn_form == 'folded':
+            sc, off = scale_offset(scope)
+            out.append(node(f'{root}/{scope}/batchnorm/mul_1', 'Mul', [src, const(sc)]))
+            out.append(node(f'{root}/{scope}/batchnorm/add_1', 'Add', [f'{root}/{scope}/batchnorm/mul_1', const(off)]))
+            return f'{root}/{scope}/batchnorm/add_1'
         refs = [const(weights[f'{scope}/{leaf}']) for leaf in ('gamma', 'beta', 'moving_mean', 'moving_variance')]
         out.append(node(f'{root}/{scope}/FusedBatchNorm', 'FusedBatchNorm', [src] + refs))
         return f'{root}/{scope}/FusedBatchNorm'

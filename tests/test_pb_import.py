@@ -59,3 +59,39 @@ def test_errors():
     bad = frozen_graph(spec, broken, perm, list(ji.names), np.asarray(ji.edges))
     with pytest.raises(ValueError):
         import_frozen_graph(bad)
+
+
+@pytest.mark.parametrize('arch,stride', [('resnet_v2_50', 32), ('resnet_v2_101', 16)])
+def test_folded_batch_norms_give_the_same_network(arch, stride):
+    """A graph whose batch norms were built from primitive ops and folded (scale inside the filters, mul_1 / add_1
+    for the pre-activations) imports as a blob that computes the same function: the oracle on the imported weights
+    equals the oracle on the original ones, and every folded scale / shift equals the original's."""
+    from oracle.metro_oracle import OracleNet
+    from metro_pose3d_b200.weights import synth_images
+    ji = exported_joint_info('h36m')
+    perm = export_permutation('h36m')
+    spec = NetSpec(arch, stride, 17)
+    w = synth_weights(spec, 5)
+    data = frozen_graph(spec, w, perm, list(ji.names), np.asarray(ji.edges), bn_form='folded')
+    m = import_frozen_graph(data)
+    assert list(m.weights) == list(w) and m.stride == stride and m.permutation == list(perm)
+    eps = 1e-5
+    for name in w:
+        if name.endswith('/gamma'):
+            scope = name[:-len('/gamma')]
+            sc0 = w[name] / np.sqrt(w[f'{scope}/moving_variance'] + eps)
+            sh0 = w[f'{scope}/beta'] - w[f'{scope}/moving_mean'] * sc0
+            sc1 = m.weights[name] / np.sqrt(m.weights[f'{scope}/moving_variance'] + eps)
+            sh1 = m.weights[f'{scope}/beta'] - m.weights[f'{scope}/moving_mean'] * sc1
+            if scope.endswith('/BatchNorm'):                 # behind a convolution: the scale moved into the filter
+                conv = scope[:-len('/BatchNorm')]
+                assert np.allclose(sc1, 1.0, rtol=0, atol=2e-7)
+                assert np.allclose(m.weights[f'{conv}/weights'], w[f'{conv}/weights'] * sc0, rtol=2e-6, atol=1e-9)
+            else:
+                assert np.allclose(sc1, sc0, rtol=2e-6, atol=0)
+            assert np.allclose(sh1, sh0, rtol=2e-6, atol=1e-7)
+    if stride == 32:
+        img = synth_images(1, seed=3)
+        a = OracleNet(spec, w, perm, 'fp64')(img)
+        b = OracleNet(spec, dict(m.weights), perm, 'fp64')(img)
+        assert np.abs(a - b).max() < 2e-3, np.abs(a - b).max()       # float32 rounding of the folded constants (measured 2e-4 mm)
