@@ -43,6 +43,17 @@ typedef enum metro_status {
  * casts to float32 (src/model/architectures.py:34). */
 typedef enum metro_dtype { METRO_F32 = 0, METRO_F16 = 1 } metro_dtype;
 
+/* Arithmetic of the backbone.  The reference exports its graph in FLAGS.dtype (src/options.py:73,
+ * src/init.py:54-59, cast at src/model/architectures.py:29): float16 by default, float32 on request.
+ *   METRO_PREC_F16        tensor-core path: float16 operands, float32 accumulation (the default export).
+ *   METRO_PREC_STRICT     every tensor float64 on CUDA cores: within float64 summation order of the exact
+ *                         graph, i.e. tighter than the float32 export (a float32 evaluation is itself
+ *                         3-5e-3 mm from the exact graph).  ~50x slower; for
+ *                         verification and accuracy-critical callers.
+ *   METRO_PREC_STRICT_F16 float64 arithmetic with the float16 graph's roundings at its storage points:
+ *                         the float16 export free of summation-order noise (verification). */
+typedef enum metro_precision { METRO_PREC_F16 = 0, METRO_PREC_STRICT = 1, METRO_PREC_STRICT_F16 = 2 } metro_precision;
+
 /* Static description of one exported model; the fields are the reference's FLAGS that shape the
  * frozen graph (src/options.py:41,96,113,118,119; src/main.py:119-127). */
 typedef struct metro_spec {
@@ -58,6 +69,12 @@ typedef struct metro_spec {
   int32_t max_batch;          /* arena is sized for this many crops per metro_infer call            */
   int32_t head_dtype;         /* metro_dtype of the head tensor kept in HBM                         */
   int32_t keep_activations;   /* debug: give every layer its own buffer (metro_debug_read)          */
+  int32_t precision;          /* metro_precision; 0 = the tensor-core float16 path                  */
+  /* the two constant fetches of the frozen graph (src/main.py:128,140-141), returned by
+   * metro_get_joint_info; both may be NULL / 0 when the caller keeps the tables itself */
+  const char *joint_names;    /* n_joints_out names in OUTPUT order, separated by '\n'               */
+  int32_t n_joint_edges;
+  const int32_t *joint_edges; /* [n_joint_edges][2] indices into the output joints                  */
 } metro_spec;
 
 typedef struct metro_handle metro_handle;
@@ -80,7 +97,19 @@ metro_status metro_plan_describe(const metro_spec *spec, char *buf, size_t buf_b
 metro_status metro_create(const metro_spec *spec, const float *weights_blob, uint64_t n_floats,
                           int32_t device, metro_handle **out);
 metro_status metro_destroy(metro_handle *h);
-metro_status metro_workspace_bytes(const metro_handle *h, uint64_t *bytes);
+/* Device bytes a handle of this model holds for batches of up to `n` crops: weights plus the
+ * activation arena, which is allocated once at create time for spec.max_batch (n <= 0 or n >
+ * max_batch report the whole arena).  No allocation ever happens inside metro_infer. */
+metro_status metro_workspace_bytes(const metro_handle *h, int32_t n, uint64_t *bytes);
+
+/* ---- the graph's two constant fetches: 'joint_names' and 'joint_edges' (inference.py:36-38,
+ *      src/main.py:128,140-141), as given in the spec at create time (dataset tables or the constants of
+ *      an imported .pb).  names_buf receives the names separated by '\n' (NUL-terminated, truncated to
+ *      names_bytes; *names_needed = bytes including the terminator); edges_buf receives up to edges_cap
+ *      (a, b) pairs; *n_edges / *n_joints the counts.  Any output pointer may be NULL. ------------- */
+metro_status metro_get_joint_info(const metro_handle *h, char *names_buf, size_t names_bytes,
+                                  size_t *names_needed, int32_t *edges_buf, int32_t edges_cap,
+                                  int32_t *n_edges, int32_t *n_joints);
 
 /* ---- inference: replaces sess.run(poses_tensor) (inference.py:25-27) --------------------------- */
 /* images_dev: device float32 NHWC [n,256,256,3] in [0,1] ('input:0', main.py:109-110)
@@ -163,7 +192,8 @@ metro_status metro_conv2d(const metro_conv_desc *d, const void *x_dev, const flo
 /* ---- debug ------------------------------------------------------------------------------------- */
 /* With spec.keep_activations: copy the named activation of the last metro_infer call to host.
  * Names: "conv1", "pool1", "<unit>/conv1", "<unit>/conv2", "<unit>/out", "<unit>/pre", "head".
- * `*elems` receives the element count; dtype is fp16 except "head" (spec.head_dtype). */
+ * `*elems` receives the element count; dtype is fp16 except "head" (spec.head_dtype); a strict-precision
+ * handle returns float64 for every name. */
 metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf, uint64_t buf_bytes,
                               uint64_t *elems);
 /* Per-launch device times (ms) of the last metro_profile call, one entry per kernel launch. */

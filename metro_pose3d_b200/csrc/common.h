@@ -1,6 +1,7 @@
 #pragma once
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include <cuda_runtime.h>
@@ -21,6 +22,24 @@ metro_status fail(metro_status st, const char *fmt, ...);
   } while (0)
 
 constexpr int kMaxJointsOut = 64;
+constexpr int kMaxDevices = 64;
+
+// One-time work per CUDA device (cudaFuncSetAttribute is per device and context): runs `f` the first time the
+// CURRENT device is seen; thread-safe.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+  template <typename F>
+  metro_status run(F &&f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return fail(METRO_ERR_CUDA, "cudaGetDevice failed");
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return METRO_OK;
+    const metro_status st = f();
+    if (st == METRO_OK) done[dev] = true;
+    return st;
+  }
+};
 
 // ---- soft-argmax ------------------------------------------------------------------------------------
 struct SoftargmaxLaunch {

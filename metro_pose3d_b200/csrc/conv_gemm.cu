@@ -626,26 +626,28 @@ EncodeTiledFn encode_fn() {
 }
 
 template <int BLOCK_N, int kMode, bool kXform = false>
-metro_status launch_t(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+metro_status launch_t(const ConvGemmParams &prm, int num_sms, cudaStream_t stream) {
+  // function attributes are per device: one opt-in per (instantiation, device), safe across threads
+  static PerDeviceOnce configured;
+  metro_status cst = configured.run([] {
     METRO_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kMode, kXform>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemLimit));
-    configured = true;
-  }
-  const int pair_tiles = ((L.prm.m_tiles + 1) / 2) * L.prm.n_tiles;
+    return METRO_OK;
+  });
+  if (cst != METRO_OK) return cst;
+  const int pair_tiles = ((prm.m_tiles + 1) / 2) * prm.n_tiles;
   if (pair_tiles == 0) return METRO_OK;
   const int max_pairs = num_sms / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // CTA pairs (cluster of 2)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kXform ? kThreadsXform : kThreads);
-  cfg.dynamicSmemBytes = size_t(L.prm.smem_bytes); cfg.stream = stream;
+  cfg.dynamicSmemBytes = size_t(prm.smem_bytes); cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   static const bool no_pdl = getenv("METRO_NO_PDL") != nullptr;
   cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-  METRO_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kMode, kXform>, L.prm));
+  METRO_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kMode, kXform>, prm));
   return METRO_OK;
 }
 
@@ -797,29 +799,29 @@ void conv_gemm_pack_weights(const float *w, int k, int cin, int cout, const floa
   }
 }
 
-metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream) {
+metro_status conv_gemm_launch(const ConvGemmLaunch &L, const ConvGemmParams &prm, int num_sms, cudaStream_t stream) {
   if (L.direct) {
     switch (L.block_n) {
-      case 160: return launch_t<160, kDirect>(L, num_sms, stream);
-      case 256: return launch_t<256, kDirect>(L, num_sms, stream);
+      case 160: return launch_t<160, kDirect>(prm, num_sms, stream);
+      case 256: return launch_t<256, kDirect>(prm, num_sms, stream);
     }
-  } else if (L.prm.has_out2) {
+  } else if (prm.has_out2) {
     switch (L.block_n) {
-      case 64: return launch_t<64, kDual>(L, num_sms, stream);
-      case 128: return launch_t<128, kDual>(L, num_sms, stream);
-      case 256: return launch_t<256, kDual>(L, num_sms, stream);
+      case 64: return launch_t<64, kDual>(prm, num_sms, stream);
+      case 128: return launch_t<128, kDual>(prm, num_sms, stream);
+      case 256: return launch_t<256, kDual>(prm, num_sms, stream);
     }
-  } else if (L.prm.ascale) {
+  } else if (prm.ascale) {
     switch (L.block_n) {
-      case 64: return launch_t<64, kSingle, true>(L, num_sms, stream);
-      case 128: return launch_t<128, kSingle, true>(L, num_sms, stream);
-      case 256: return launch_t<256, kSingle, true>(L, num_sms, stream);
+      case 64: return launch_t<64, kSingle, true>(prm, num_sms, stream);
+      case 128: return launch_t<128, kSingle, true>(prm, num_sms, stream);
+      case 256: return launch_t<256, kSingle, true>(prm, num_sms, stream);
     }
   } else {
     switch (L.block_n) {
-      case 64: return launch_t<64, kSingle>(L, num_sms, stream);
-      case 128: return launch_t<128, kSingle>(L, num_sms, stream);
-      case 256: return launch_t<256, kSingle>(L, num_sms, stream);
+      case 64: return launch_t<64, kSingle>(prm, num_sms, stream);
+      case 128: return launch_t<128, kSingle>(prm, num_sms, stream);
+      case 256: return launch_t<256, kSingle>(prm, num_sms, stream);
     }
   }
   return fail(METRO_ERR_INTERNAL, "conv_gemm: unsupported BLOCK_N %d", L.block_n);

@@ -73,7 +73,9 @@ metro_status conv_gemm_plan_smem(ConvGemmLaunch &L, int k_blocks);
 // Fills the M-tiling fields for `n` images (crops n_base .. n_base + n of the buffers) of an out_side x out_side output.
 metro_status conv_gemm_set_batch(ConvGemmParams &p, int n, int n_base = 0);
 metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side);
-metro_status conv_gemm_launch(const ConvGemmLaunch &L, int num_sms, cudaStream_t stream);
+// `prm` = L.prm with this call's batch slice / direction / profiling pointer filled in (L itself is never mutated
+// after it is built, so launches are capture-safe).
+metro_status conv_gemm_launch(const ConvGemmLaunch &L, const ConvGemmParams &prm, int num_sms, cudaStream_t stream);
 // Packs HWIO float32 filters into [cout_pad][K] fp16 in the kernel's K-block order; `w2` (1x1,
 // [cin2][cout]) is appended along K.
 void conv_gemm_pack_weights(const float *w_hwio, int k, int cin, int cout, const float *w2, int cin2,

@@ -12,6 +12,7 @@
 #include "conv_gemm.h"
 #include "plan.h"
 #include "root_fused.h"
+#include "strict.h"
 
 namespace metro {
 
@@ -53,7 +54,7 @@ void bn_affine(const float *bn, int c, std::vector<float> &scale, std::vector<fl
 
 struct DeviceArena {
   std::vector<void *> ptrs;
-  size_t total = 0;
+  size_t total = 0, uploaded = 0;   // uploaded: constants (weights, per-channel vectors), independent of the batch
   ~DeviceArena() { for (void *p : ptrs) cudaFree(p); }
   metro_status alloc(void **out, size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -71,6 +72,7 @@ struct DeviceArena {
     if (st != METRO_OK) return st;
     METRO_CUDA(cudaMemset(p, 0, n * sizeof(T)));
     METRO_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    uploaded += (n ? n : 1) * sizeof(T);
     *out = static_cast<T *>(p);
     return METRO_OK;
   }
@@ -220,6 +222,12 @@ struct metro_handle {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   float *stage_img = nullptr, *stage_pose = nullptr;
+  bool host_ready = false;  // every resource of the host-buffer path exists (set last, so a failed first call retries)
+  StrictNet *strict = nullptr;   // precision != METRO_PREC_F16: the float64 CUDA-core evaluation (strict.cu)
+  std::string joint_names;       // the graph's constant fetches (main.py:128,140-141), '\n'-separated
+  std::vector<int32_t> joint_edges;
+  size_t weight_bytes = 0;       // part of arena.total that does not scale with max_batch
+  int stem_chunk = 0;            // METRO_STEM_CHUNK: metro_infer runs the stem in slices of this many crops (0 = whole batch)
   int alternate = 1;      // consecutive convolutions walk their tile lists in opposite directions (METRO_NO_ALTERNATE)
   int host_chunk = 64;    // crops per PCIe slice of metro_infer_host (METRO_HOST_CHUNK)
   int host_slice_u8 = 128;  // stem and tail slice of metro_infer_host_u8: a quarter of the bytes per crop, so larger
@@ -238,6 +246,16 @@ metro_status check_spec(const metro_spec *spec) {
     if (spec->permutation[i] < 0 || spec->permutation[i] >= spec->n_joints_model)
       return fail(METRO_ERR_VALUE, "permutation[%d]=%d out of range", i, spec->permutation[i]);
   if (spec->head_dtype != METRO_F32 && spec->head_dtype != METRO_F16) return fail(METRO_ERR_VALUE, "bad head_dtype");
+  if (spec->precision < METRO_PREC_F16 || spec->precision > METRO_PREC_STRICT_F16) return fail(METRO_ERR_VALUE, "bad precision");
+  if (spec->n_joint_edges < 0 || (spec->n_joint_edges > 0 && !spec->joint_edges)) return fail(METRO_ERR_VALUE, "bad joint_edges");
+  for (int i = 0; i < 2 * spec->n_joint_edges; ++i)
+    if (spec->joint_edges[i] < 0 || spec->joint_edges[i] >= spec->n_joints_out)
+      return fail(METRO_ERR_VALUE, "joint_edges[%d]=%d out of range [0,%d)", i, spec->joint_edges[i], spec->n_joints_out);
+  if (spec->joint_names) {
+    int lines = 1;
+    for (const char *c = spec->joint_names; *c; ++c) lines += *c == '\n';
+    if (lines != spec->n_joints_out) return fail(METRO_ERR_VALUE, "joint_names holds %d names for %d output joints", lines, spec->n_joints_out);
+  }
   return METRO_OK;
 }
 
@@ -388,6 +406,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
   if (getenv("METRO_NO_ALTERNATE")) h.alternate = 0;
   if (const char *e = getenv("METRO_HOST_CHUNK")) h.host_chunk = h.host_slice_u8 = atoi(e);
   if (const char *e = getenv("METRO_HOST_TAIL")) h.host_tail = atoi(e);
+  if (const char *e = getenv("METRO_STEM_CHUNK")) h.stem_chunk = atoi(e);
   // ---- logits (resnet_v2.py:234-236) -> head tensor ----
   {
     const size_t eh = size_t(pl.feat_side) * pl.feat_side * pl.logits.cout;
@@ -414,6 +433,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     if ((st = A.alloc(&h.sam_ws, ws)) != METRO_OK) return st;
     METRO_CUDA(cudaMemset(h.sam_ws, 0, ws));
   }
+  h.weight_bytes = A.uploaded;
   METRO_CUDA(cudaDeviceSynchronize());
   return METRO_OK;
 }
@@ -443,11 +463,15 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
                               (t && t->role_prof) ? t->role_prof : nullptr)) != METRO_OK) return st;
   mark("conv1+pool1");
   for (int li = 0; li < stem_gemms; ++li) {
-    ConvGemmLaunch &L = h->gemms[li];
-    conv_gemm_set_batch(L.prm, n, n_base);
-    L.prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;     // the root kernel walks forwards
-    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
-    if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
+    // the handle's launch record is never written after metro_create: the batch slice, walk direction and
+    // profiling pointer of THIS call travel in the by-value kernel parameters (so a call can be captured
+    // into a CUDA graph, and two streams may use one handle's weights concurrently with separate arenas)
+    const ConvGemmLaunch &L = h->gemms[li];
+    ConvGemmParams prm = L.prm;
+    conv_gemm_set_batch(prm, n, n_base);
+    prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;     // the root kernel walks forwards
+    prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
+    if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
   return METRO_OK;
@@ -463,11 +487,12 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
     t->ev.push_back(e); t->names.push_back(name);
   };
   for (size_t li = first_gemm; li < h->gemms.size(); ++li) {
-    ConvGemmLaunch &L = h->gemms[li];
-    conv_gemm_set_batch(L.prm, n, n_base);
-    L.prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;
-    L.prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
-    if ((st = conv_gemm_launch(L, h->num_sms, s)) != METRO_OK) return st;
+    const ConvGemmLaunch &L = h->gemms[li];
+    ConvGemmParams prm = L.prm;
+    conv_gemm_set_batch(prm, n, n_base);
+    prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;
+    prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
+    if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
   SoftargmaxLaunch sl = h->sam;
@@ -493,6 +518,19 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
   if (t) {
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
     t->ev.push_back(e); t->names.push_back("start");
+  }
+  if (h->strict) return strict_run(h->strict, images, u8, n, poses, s);
+  if (h->stem_chunk > 0 && h->stem_chunk < n && !t) {
+    // experiment knob: the stem (maps of 32x32 and larger, HBM-bound) in slices small enough for a layer's
+    // output to still sit in L2 when the next layer reads it; the deep blocks once on the whole batch
+    const size_t img_bytes = size_t(h->plan.proc_side) * h->plan.proc_side * 3 * (u8 ? 1 : 4);
+    for (int lo = 0; lo < n; lo += h->stem_chunk) {
+      const int cnt = std::min(h->stem_chunk, n - lo);
+      metro_status st = run_stem(h, static_cast<const unsigned char *>(images) + size_t(lo) * img_bytes, u8, cnt, lo,
+                                 h->stem_gemms, s, nullptr);
+      if (st != METRO_OK) return st;
+    }
+    return run_tail(h, n, 0, h->stem_gemms, poses, s, nullptr);
   }
   metro_status st = run_stem(h, images, u8, n, 0, 0, s, t);
   if (st != METRO_OK) return st;
@@ -557,6 +595,17 @@ metro_status metro_create(const metro_spec *spec, const float *weights_blob, uin
   h->spec = *spec;
   h->perm.assign(spec->permutation, spec->permutation + spec->n_joints_out);
   h->spec.permutation = h->perm.data();
+  if (spec->joint_names) h->joint_names = spec->joint_names;
+  if (spec->n_joint_edges > 0) h->joint_edges.assign(spec->joint_edges, spec->joint_edges + 2 * spec->n_joint_edges);
+  h->spec.joint_names = nullptr; h->spec.joint_edges = nullptr;     // the handle keeps its own copies
+  if (spec->precision != METRO_PREC_F16) {
+    st = strict_build(h->plan, weights_blob, h->max_batch, spec->precision == METRO_PREC_STRICT_F16 ? 1 : 0, spec->box_size_mm,
+                      h->perm, spec->keep_activations != 0, &h->strict);
+    if (st != METRO_OK) return st;
+    METRO_CUDA(cudaDeviceSynchronize());
+    *out = h.release();
+    return METRO_OK;
+  }
   st = build_handle(*h, weights_blob);
   if (st != METRO_OK) return st;
   *out = h.release();
@@ -571,13 +620,36 @@ metro_status metro_destroy(metro_handle *h) {
   for (auto e : h->ev_copied) if (e) cudaEventDestroy(e);
   if (h->stage_img) cudaFree(h->stage_img);
   if (h->stage_pose) cudaFree(h->stage_pose);
+  if (h->strict) strict_destroy(h->strict);
   delete h;
   return METRO_OK;
 }
 
-metro_status metro_workspace_bytes(const metro_handle *h, uint64_t *bytes) {
+metro_status metro_workspace_bytes(const metro_handle *h, int32_t n, uint64_t *bytes) {
   if (!h || !bytes) return fail(METRO_ERR_VALUE, "null argument");
-  *bytes = h->arena.total;
+  const size_t total = h->strict ? strict_bytes(h->strict) : h->arena.total;
+  if (n <= 0 || n >= h->max_batch || h->strict) { *bytes = total; return METRO_OK; }
+  // weights and per-channel vectors do not scale with the batch; every activation buffer is `max_batch` crops long
+  *bytes = h->weight_bytes + (total - h->weight_bytes) / uint64_t(h->max_batch) * uint64_t(n);
+  return METRO_OK;
+}
+
+metro_status metro_get_joint_info(const metro_handle *h, char *names_buf, size_t names_bytes, size_t *names_needed,
+                                  int32_t *edges_buf, int32_t edges_cap, int32_t *n_edges, int32_t *n_joints) {
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  if (h->joint_names.empty() && h->joint_edges.empty())
+    return fail(METRO_ERR_VALUE, "this handle was created without joint tables (spec.joint_names / spec.joint_edges)");
+  if (names_needed) *names_needed = h->joint_names.size() + 1;
+  if (names_buf && names_bytes > 0) {
+    const size_t k = std::min(names_bytes - 1, h->joint_names.size());
+    std::memcpy(names_buf, h->joint_names.data(), k);
+    names_buf[k] = 0;
+  }
+  const int32_t ne = int32_t(h->joint_edges.size() / 2);
+  if (n_edges) *n_edges = ne;
+  if (n_joints) *n_joints = int32_t(h->perm.size());
+  if (edges_buf && edges_cap > 0)
+    std::memcpy(edges_buf, h->joint_edges.data(), size_t(std::min(ne, edges_cap)) * 2 * sizeof(int32_t));
   return METRO_OK;
 }
 
@@ -612,14 +684,23 @@ metro_status infer_host(metro_handle *h, const void *images_host_v, bool u8, int
   const size_t img_elems = size_t(h->plan.proc_side) * h->plan.proc_side * 3;
   const size_t img_bytes = img_elems * (u8 ? sizeof(uint8_t) : sizeof(float));   // this call's element size
   const size_t pose_bytes = h->perm.size() * 3 * sizeof(float);
-  if (!h->stream) {
-    METRO_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    METRO_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    METRO_CUDA(cudaMalloc(&h->stage_img, img_elems * sizeof(float) * h->max_batch));
-    METRO_CUDA(cudaMalloc(&h->stage_pose, pose_bytes * h->max_batch));
-    for (int i = 0; i < 2; ++i) {
-      METRO_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
-    }
+  if (!h->host_ready) {
+    // a failed allocation returns early and leaves host_ready unset: the next call resumes where this one stopped
+    if (!h->stream) METRO_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (!h->copy_stream) METRO_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->stage_img) METRO_CUDA(cudaMalloc(&h->stage_img, img_elems * sizeof(float) * h->max_batch));
+    if (!h->stage_pose) METRO_CUDA(cudaMalloc(&h->stage_pose, pose_bytes * h->max_batch));
+    for (int i = 0; i < 2; ++i)
+      if (!h->ev_copied[i]) METRO_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    h->host_ready = true;
+  }
+  if (h->strict) {
+    METRO_CUDA(cudaMemcpyAsync(h->stage_img, images_host, img_bytes * n, cudaMemcpyHostToDevice, h->stream));
+    metro_status sst = strict_run(h->strict, h->stage_img, u8, n, h->stage_pose, h->stream);
+    if (sst != METRO_OK) return sst;
+    METRO_CUDA(cudaMemcpyAsync(poses_host, h->stage_pose, pose_bytes * n, cudaMemcpyDeviceToHost, h->stream));
+    METRO_CUDA(cudaStreamSynchronize(h->stream));
+    return METRO_OK;
   }
   // The crops arrive over PCIe in slices; the stem of the network (root, block1, block2: the layers whose
   // tile count per crop is large, so that a slice still fills the GPU) runs slice by slice underneath the
@@ -769,7 +850,7 @@ metro_status metro_conv2d(const metro_conv_desc *d, const void *x_dev, const flo
   metro_status st = build_gemm(arena, g, L);
   if (st != METRO_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  st = conv_gemm_launch(L, prop.multiProcessorCount, s);
+  st = conv_gemm_launch(L, L.prm, prop.multiProcessorCount, s);
   if (st != METRO_OK) return st;
   METRO_CUDA(cudaStreamSynchronize(s));   // temporaries (packed weights) are freed on return
   return METRO_OK;
@@ -777,6 +858,19 @@ metro_status metro_conv2d(const metro_conv_desc *d, const void *x_dev, const flo
 
 metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf, uint64_t buf_bytes, uint64_t *elems) {
   if (!h || !name) return fail(METRO_ERR_VALUE, "null argument");
+  if (h->strict) {
+    const double *ptr = nullptr; size_t per = 0;
+    if (!strict_debug(h->strict, name, &ptr, &per)) return fail(METRO_ERR_VALUE, "no activation named '%s'", name);
+    const uint64_t n_el = uint64_t(per) * h->max_batch;
+    if (elems) *elems = n_el;
+    if (host_buf) {
+      if (buf_bytes < n_el * 8) return fail(METRO_ERR_VALUE, "buffer too small: need %llu bytes", (unsigned long long)(n_el * 8));
+      METRO_CUDA(cudaSetDevice(h->device));
+      METRO_CUDA(cudaDeviceSynchronize());
+      METRO_CUDA(cudaMemcpy(host_buf, ptr, n_el * 8, cudaMemcpyDeviceToHost));
+    }
+    return METRO_OK;
+  }
   auto it = h->debug.find(name);
   if (it == h->debug.end() || !it->second.first) return fail(METRO_ERR_VALUE, "no activation named '%s'", name);
   const bool is_head = std::string(name) == "head";
@@ -794,6 +888,10 @@ metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf,
 
 metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launches) {
   if (!h || !launches) return fail(METRO_ERR_VALUE, "null argument");
+  if (h->strict) {   // image cast + one kernel per conv / BN / pool step + decode + metric (strict.cu)
+    *launches = n > 0 ? int32_t(h->plan.n_convs() + h->plan.units.size() + 2 + 3) : 0;
+    return METRO_OK;
+  }
   *launches = n > 0 ? int32_t(h->gemms.size()) + 3 : 0;   // + image pack, fused root, soft-argmax
   return METRO_OK;
 }
@@ -802,6 +900,7 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
                            char *names_buf, size_t names_bytes, int32_t *n_launches) {
   Timer t;
   if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  if (h->strict) return fail(METRO_ERR_VALUE, "metro_profile: per-launch timing exists for the tensor-core path only");
   const bool roles = getenv("METRO_ROLE_PROF") != nullptr;
   const size_t role_elems = size_t(h->gemms.size() + 1) * h->num_sms * 16;
   if (roles) {

@@ -409,11 +409,12 @@ metro_status root_fused_launch(const void *image_map, const __half *wpack, const
                                const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base,
                                int num_sms, cudaStream_t stream, long long *prof) {
   if (n == 0) return METRO_OK;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;     // function attributes are per device
+  metro_status cst = configured.run([] {
     METRO_CUDA(cudaFuncSetAttribute(root_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+    return METRO_OK;
+  });
+  if (cst != METRO_OK) return cst;
   RootParams p;
   p.pmap = *static_cast<const CUtensorMap *>(image_map);
   p.wpack = wpack; p.bias = bias; p.pscale = pscale; p.pshift = pshift;

@@ -454,12 +454,13 @@ size_t smem_bytes(const SoftargmaxLaunch &L) {
 
 template <int VEC, bool F16, int CH, int MAXT, int MINB>
 metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
-  static size_t configured = 0;
-  const size_t sm = smem_bytes(L);
-  if (configured < sm) {
+  static PerDeviceOnce configured;     // function attributes are per device
+  const size_t sm = smem_bytes(L);     // softargmax_plan caps it at 100 KB
+  metro_status cst = configured.run([] {
     METRO_CUDA(cudaFuncSetAttribute(softargmax_kernel<VEC, F16, CH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = 100 * 1024;
-  }
+    return METRO_OK;
+  });
+  if (cst != METRO_OK) return cst;
   const dim3 grid(unsigned(L.n) * unsigned(L.splits)), block(unsigned((L.slots * L.lanes + 31) & ~31));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = sm; cfg.stream = stream;

@@ -37,20 +37,75 @@ class ShardedPoseEstimator:
         lo, hi = shard_bounds(n_total, self.world, self.rank)
         return slice(lo, hi)
 
-    def gather(self, local, n_total: int):
-        """All-gather ragged shards into [n_total, J, 3] (pads to the largest shard, then trims)."""
-        import torch
-        if self.world == 1:
-            return local
+    def _buffers(self, local, cap):
+        """Gather buffers are allocated once per (shape, device) and re-used: no allocation in the step."""
+        key = (cap, local.dtype, local.device)
+        if getattr(self, '_key', None) != key:
+            import torch
+            self._key = key
+            self._pad = torch.zeros((cap, self.j, 3), dtype=local.dtype, device=local.device)
+            self._out = [torch.empty((self.world * cap, self.j, 3), dtype=local.dtype, device=local.device) for _ in range(2)]
+            self._turn = 0
+            if local.is_cuda:
+                self._stream = torch.cuda.Stream(device=local.device)
+                self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+                self._done = [None, None]
+        return self._pad, self._out
+
+    def _collect(self, local, n_total: int, out):
         sizes = [shard_bounds(n_total, self.world, r) for r in range(self.world)]
         cap = max(hi - lo for lo, hi in sizes)
-        buf = torch.zeros((cap, self.j, 3), dtype=local.dtype, device=local.device)
-        buf[:local.shape[0]] = local
-        out = torch.empty((self.world * cap, self.j, 3), dtype=local.dtype, device=local.device)
-        self.dist.all_gather_into_tensor(out, buf, group=self.group)
+        src = local
+        if local.shape[0] != cap:                       # ragged shard: pad to the largest
+            self._pad[:local.shape[0]] = local
+            src = self._pad
+        self.dist.all_gather_into_tensor(out, src.contiguous(), group=self.group)
         if all(hi - lo == cap for lo, hi in sizes):
             return out
+        import torch
         return torch.cat([out[r * cap:r * cap + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+
+    def gather(self, local, n_total: int):
+        """All-gather ragged shards into [n_total, J, 3] (pads to the largest shard, then trims)."""
+        if self.world == 1:
+            return local
+        cap = max(hi - lo for lo, hi in (shard_bounds(n_total, self.world, r) for r in range(self.world)))
+        _, outs = self._buffers(local, cap)
+        return self._collect(local, n_total, outs[0])
+
+    def gather_async(self, local, n_total: int):
+        """The same exchange issued on a side stream, so that it runs underneath the NEXT step's kernels instead of
+        holding the launch stream at a per-step rendezvous.  The caller alternates between two `local` buffers; the
+        result is valid after ``wait()`` (or after the next-but-one call returns)."""
+        if self.world == 1 or not local.is_cuda:
+            return self.gather(local, n_total)
+        import torch
+        cap = max(hi - lo for lo, hi in (shard_bounds(n_total, self.world, r) for r in range(self.world)))
+        _, outs = self._buffers(local, cap)
+        t = self._turn
+        self._turn ^= 1
+        cur = torch.cuda.current_stream(local.device)
+        self._ready[t].record(cur)                      # `local` is complete at this point of the launch stream
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(self._ready[t])
+            res = self._collect(local, n_total, outs[t])
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        # the launch stream may overwrite `local`'s twin (the other buffer) freely; before THIS buffer is written
+        # again (two steps from now) the gather that reads it must have finished
+        if self._done[t ^ 1] is not None:
+            cur.wait_event(self._done[t ^ 1])
+        self._done[t] = ev
+        return res
+
+    def wait(self):
+        """Joins every outstanding asynchronous gather into the current stream."""
+        if self.world == 1 or getattr(self, '_done', None) is None:
+            return
+        import torch
+        for ev in self._done:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
 
     def __call__(self, images_global):
         n_total = images_global.shape[0]

@@ -33,19 +33,27 @@ class MetroModel:
     def __init__(self, arch: str = 'resnet_v2_50', stride: int = 16, dataset: str = 'h36m',
                  weights=None, max_batch: int = 256, device: int = 0, head_dtype: str = 'f32',
                  keep_activations: bool = False, seed: int = 0, n_joints_model: Optional[int] = None,
-                 permutation: Optional[Sequence[int]] = None):
+                 permutation: Optional[Sequence[int]] = None, precision: str = 'f16', joint_info=None):
+        """``precision``: 'f16' = the tensor-core path (the reference's default float16 export, src/options.py:73);
+        'strict' = float64 on CUDA cores (tighter than the reference's ``--dtype float32`` export; slow, for
+        verification); 'strict_f16' = float64 arithmetic with the float16 graph's storage roundings."""
         self.lib = _lib.load()
         self.dataset = dataset
         ji = model_joint_info(dataset)
         self.n_joints_model = n_joints_model or ji.n_joints
         self.permutation = list(permutation) if permutation is not None else export_permutation(dataset)
-        self.joint_info = exported_joint_info(dataset) if permutation is None else None
+        if joint_info is None and permutation is None:
+            joint_info = exported_joint_info(dataset)
         self.spec = NetSpec(arch, stride, self.n_joints_model)      # raises ValueError like the reference
         self.device = device
         self.max_batch = max_batch
+        self.precision = precision
         self.head_dtype = {'f32': _lib.METRO_F32, 'f16': _lib.METRO_F16}[head_dtype]
         self._cspec = _lib.make_spec(arch, stride, self.n_joints_model, self.permutation, max_batch,
-                                     head_dtype=self.head_dtype, keep_activations=keep_activations)
+                                     head_dtype=self.head_dtype, keep_activations=keep_activations,
+                                     precision=_lib.PRECISIONS[precision],
+                                     joint_names=None if joint_info is None else list(joint_info.names),
+                                     joint_edges=None if joint_info is None else list(joint_info.edges))
         if weights is None:
             weights = synth_weights(self.spec, seed)
         blob = weights if isinstance(weights, np.ndarray) else pack_blob(self.spec, weights)
@@ -59,7 +67,7 @@ class MetroModel:
 
     @classmethod
     def from_frozen_graph(cls, path_or_bytes, max_batch: int = 256, device: int = 0, head_dtype: str = 'f32',
-                          keep_activations: bool = False) -> 'MetroModel':
+                          keep_activations: bool = False, precision: str = 'f16') -> 'MetroModel':
         """Loads a model exported by the reference's ``main.export()`` (src/main.py:106-160): the binary GraphDef
         is read without TensorFlow (``pb_import``), its constants become the weight blob, its ``output`` gather
         indices the permutation and its ``joint_names`` / ``joint_edges`` constants the joint tables."""
@@ -67,21 +75,32 @@ class MetroModel:
         from .pb_import import import_frozen_graph, load_frozen_model
         fm = import_frozen_graph(path_or_bytes) if isinstance(path_or_bytes, (bytes, bytearray)) \
             else load_frozen_model(path_or_bytes)
+        ji = JointInfo(list(fm.joint_names), [tuple(int(v) for v in e) for e in fm.joint_edges])
         model = cls(fm.arch, fm.stride, dataset='h36m', weights=fm.weights, max_batch=max_batch, device=device,
                     head_dtype=head_dtype, keep_activations=keep_activations, n_joints_model=fm.n_joints_model,
-                    permutation=fm.permutation)
+                    permutation=fm.permutation, precision=precision, joint_info=ji)
         model.dataset = 'frozen-graph'
-        model.joint_info = JointInfo(fm.joint_names, [tuple(int(v) for v in e) for e in fm.joint_edges])
         return model
 
     # -- the three fetches of the frozen graph ----------------------------------------------------
+    def _joint_info(self):
+        """'joint_names' / 'joint_edges' through the C-ABI (metro_get_joint_info): the handle holds the tables it was
+        created with, whether they came from a dataset or from the constants of an imported .pb."""
+        need, ne, nj = C.c_size_t(0), C.c_int32(0), C.c_int32(0)
+        _lib.check(self.lib.metro_get_joint_info(self._h, None, 0, C.byref(need), None, 0, C.byref(ne), C.byref(nj)))
+        buf = C.create_string_buffer(need.value)
+        edges = (C.c_int32 * max(2 * ne.value, 1))()
+        _lib.check(self.lib.metro_get_joint_info(self._h, buf, need.value, None, edges, ne.value, None, None))
+        names = buf.value.decode().split('\n') if need.value > 1 else []
+        return names, np.asarray(list(edges)[:2 * ne.value], dtype=np.int64).reshape(-1, 2)
+
     @property
     def joint_names(self):
-        return list(self.joint_info.names)
+        return self._joint_info()[0]
 
     @property
     def joint_edges(self) -> np.ndarray:
-        return np.asarray(self.joint_info.edges, dtype=np.int64)
+        return self._joint_info()[1]
 
     @property
     def n_joints_out(self) -> int:
@@ -101,10 +120,17 @@ class MetroModel:
         n = images.shape[0]
         if out is None:
             out = torch.empty((n, self.n_joints_out, 3), dtype=torch.float32, device=images.device)
+        elif (tuple(out.shape) != (n, self.n_joints_out, 3) or out.dtype != torch.float32 or not out.is_contiguous()
+              or out.device != images.device):
+            raise ValueError(f'out must be a contiguous float32 [{n},{self.n_joints_out},3] tensor on {images.device}')
         if stream is None:
             stream = torch.cuda.current_stream(images.device).cuda_stream
         fn = self.lib.metro_infer_u8 if images.dtype == torch.uint8 else self.lib.metro_infer
-        _lib.check(fn(self._h, images.data_ptr(), n, out.data_ptr(), stream))
+        # the frozen graph's placeholder is [None,256,256,3] (main.py:109-110): any batch is accepted, in pieces of
+        # at most max_batch crops (the arena's size)
+        for lo in range(0, n, self.max_batch):
+            cnt = min(self.max_batch, n - lo)
+            _lib.check(fn(self._h, images[lo:lo + cnt].data_ptr(), cnt, out[lo:lo + cnt].data_ptr(), stream))
         return out
 
     def infer_host(self, images: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -122,8 +148,13 @@ class MetroModel:
             out = np.empty((n, self.n_joints_out, 3), dtype=np.float32)
         elif hasattr(out, 'numpy'):
             out = out.numpy()
+        if out.shape != (n, self.n_joints_out, 3) or out.dtype != np.float32 or not out.flags['C_CONTIGUOUS']:
+            raise ValueError(f'out must be a C-contiguous float32 [{n},{self.n_joints_out},3] array')
         fn = self.lib.metro_infer_host_u8 if images.dtype == np.uint8 else self.lib.metro_infer_host
-        _lib.check(fn(self._h, images.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p)))
+        for lo in range(0, n, self.max_batch):          # any batch size, like the graph's [None,...] placeholder
+            cnt = min(self.max_batch, n - lo)
+            _lib.check(fn(self._h, images[lo:lo + cnt].ctypes.data_as(C.c_void_p), cnt,
+                          out[lo:lo + cnt].ctypes.data_as(C.c_void_p)))
         return out
 
     def __call__(self, images):
@@ -138,7 +169,9 @@ class MetroModel:
         n = C.c_uint64(0)
         _lib.check(self.lib.metro_debug_read(self._h, name.encode(), None, 0, C.byref(n)))
         dt = np.float16
-        if name == 'head' and self.head_dtype == _lib.METRO_F32:
+        if self.precision != 'f16':
+            dt = np.float64
+        elif name == 'head' and self.head_dtype == _lib.METRO_F32:
             dt = np.float32
         buf = np.empty(n.value, dtype=dt)
         _lib.check(self.lib.metro_debug_read(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes, None))
@@ -161,10 +194,11 @@ class MetroModel:
         _lib.check(self.lib.metro_launch_count(self._h, n, C.byref(k)))
         return k.value
 
-    def workspace_bytes(self) -> int:
-        n = C.c_uint64(0)
-        _lib.check(self.lib.metro_workspace_bytes(self._h, C.byref(n)))
-        return n.value
+    def workspace_bytes(self, n: int = 0) -> int:
+        """Device bytes the handle holds for batches of up to ``n`` crops (0 = its whole arena)."""
+        b = C.c_uint64(0)
+        _lib.check(self.lib.metro_workspace_bytes(self._h, n, C.byref(b)))
+        return b.value
 
     def close(self):
         if getattr(self, '_h', None):
@@ -178,7 +212,9 @@ class MetroModel:
             pass
 
 
-_loaded = {}
+_loaded = {}              # (path, device) -> MetroModel
+_MAX_LOADED = 4
+_DEFAULT_MAX_BATCH = 64
 
 
 def estimate_pose(images, model) -> Tuple[object, np.ndarray, list]:
@@ -186,10 +222,15 @@ def estimate_pose(images, model) -> Tuple[object, np.ndarray, list]:
     (poses [N,J,3] mm, joint_edges [E,2] int64, joint_names [J]).  ``model`` is a ``MetroModel`` or, as in the
     reference, the path of an exported ``.pb`` file (loaded once per path)."""
     if isinstance(model, (str, bytes)) and not isinstance(model, MetroModel):
-        key = model
+        dev = images.device.index if getattr(images, 'is_cuda', False) else None
+        if dev is None:
+            dev = _torch().cuda.current_device()
+        key = (model, dev)
         if key not in _loaded:
-            n = int(images.shape[0])
-            _loaded[key] = MetroModel.from_frozen_graph(model, max_batch=max(n, 1))
+            while len(_loaded) >= _MAX_LOADED:          # bounded: least recently loaded model goes first
+                _loaded.pop(next(iter(_loaded))).close()
+            # larger batches are processed in pieces of max_batch crops (MetroModel.infer / infer_host)
+            _loaded[key] = MetroModel.from_frozen_graph(model, max_batch=_DEFAULT_MAX_BATCH, device=dev)
         model = _loaded[key]
     return model(images), model.joint_edges, model.joint_names
 

@@ -16,10 +16,12 @@ LIB_PATH = os.path.join(_HERE, 'libmetro.so')
 
 METRO_OK, METRO_ERR_VALUE, METRO_ERR_CUDA, METRO_ERR_NO_DEVICE, METRO_ERR_NOMEM, METRO_ERR_INTERNAL = range(6)
 METRO_F32, METRO_F16 = 0, 1
+METRO_PREC_F16, METRO_PREC_STRICT, METRO_PREC_STRICT_F16 = 0, 1, 2
+PRECISIONS = {'f16': METRO_PREC_F16, 'strict': METRO_PREC_STRICT, 'strict_f16': METRO_PREC_STRICT_F16}
 
 EXPORTS = [
     'metro_last_error', 'metro_version', 'metro_blob_floats', 'metro_plan_describe', 'metro_create',
-    'metro_destroy', 'metro_workspace_bytes', 'metro_infer', 'metro_infer_host', 'metro_infer_u8', 'metro_infer_host_u8', 'metro_to_orig_cam',
+    'metro_destroy', 'metro_workspace_bytes', 'metro_get_joint_info', 'metro_infer', 'metro_infer_host', 'metro_infer_u8', 'metro_infer_host_u8', 'metro_to_orig_cam',
     'metro_softargmax_workspace_bytes', 'metro_softargmax', 'metro_conv2d', 'metro_debug_read',
     'metro_profile', 'metro_launch_count',
 ]
@@ -30,7 +32,8 @@ class MetroSpec(C.Structure):
         ('arch', C.c_int32), ('stride', C.c_int32), ('n_joints_model', C.c_int32), ('depth', C.c_int32),
         ('centered_stride', C.c_int32), ('proc_side', C.c_int32), ('box_size_mm', C.c_float),
         ('n_joints_out', C.c_int32), ('permutation', C.POINTER(C.c_int32)), ('max_batch', C.c_int32),
-        ('head_dtype', C.c_int32), ('keep_activations', C.c_int32),
+        ('head_dtype', C.c_int32), ('keep_activations', C.c_int32), ('precision', C.c_int32),
+        ('joint_names', C.c_char_p), ('n_joint_edges', C.c_int32), ('joint_edges', C.POINTER(C.c_int32)),
     ]
 
 
@@ -85,7 +88,9 @@ def load() -> C.CDLL:
     lib.metro_plan_describe.argtypes = [C.POINTER(MetroSpec), C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.metro_create.argtypes = [C.POINTER(MetroSpec), vp, u64, i32, C.POINTER(vp)]
     lib.metro_destroy.argtypes = [vp]
-    lib.metro_workspace_bytes.argtypes = [vp, C.POINTER(u64)]
+    lib.metro_workspace_bytes.argtypes = [vp, i32, C.POINTER(u64)]
+    lib.metro_get_joint_info.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(i32), i32,
+                                         C.POINTER(i32), C.POINTER(i32)]
     lib.metro_infer.argtypes = [vp, vp, i32, vp, vp]
     lib.metro_infer_u8.argtypes = [vp, vp, i32, vp, vp]
     lib.metro_infer_host.argtypes = [vp, vp, i32, vp]
@@ -118,15 +123,20 @@ def check(status: int):
 
 def make_spec(arch: str, stride: int, n_joints_model: int, permutation: Sequence[int], max_batch: int = 1,
               depth: int = 8, centered_stride: bool = True, proc_side: int = 256, box_size_mm: float = 2200.0,
-              head_dtype: int = METRO_F32, keep_activations: bool = False):
+              head_dtype: int = METRO_F32, keep_activations: bool = False, precision: int = METRO_PREC_F16,
+              joint_names: Optional[Sequence[str]] = None, joint_edges=None):
     archs = {'resnet_v2_50': 50, 'resnet_v2_101': 101}
     if arch not in archs:
         raise ValueError(f'unknown architecture {arch!r}')
     perm = (C.c_int32 * len(permutation))(*permutation)
+    names = None if joint_names is None else '\n'.join(joint_names).encode()
+    flat = [] if joint_edges is None else [int(v) for e in joint_edges for v in e]
+    edges = (C.c_int32 * max(len(flat), 1))(*flat)
     spec = MetroSpec(archs[arch], stride, n_joints_model, depth, int(centered_stride), proc_side,
                      box_size_mm, len(permutation), C.cast(perm, C.POINTER(C.c_int32)), max_batch, head_dtype,
-                     int(keep_activations))
-    spec._perm_keepalive = perm
+                     int(keep_activations), precision, names, len(flat) // 2,
+                     C.cast(edges, C.POINTER(C.c_int32)) if flat else None)
+    spec._keepalive = (perm, names, edges)
     return spec
 
 

@@ -38,6 +38,10 @@ def _worker(rank, world, port, n, q):
 
     est = ShardedPoseEstimator(infer, 17)
     out = est(x)
+    # the asynchronous variant (side-stream gather on a GPU; same exchange on CPU tensors) and re-used buffers
+    again = est.gather_async(infer(x[est.local_slice(n)]), n)
+    est.wait()
+    assert torch.equal(again, out)
     if rank == 0:
         q.put(out.numpy())
     dist.barrier()

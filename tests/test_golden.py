@@ -136,10 +136,10 @@ def test_cuda_decode_matches_reference_code(case):
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['rn50_s32', 'rn50_s16'])
 def test_cuda_graph_against_reference_code(name):
-    """The whole CUDA path against the reference-code poses (float64 evaluation of the graph).  The
-    CUDA path computes the backbone in float16 like the reference's default (src/options.py:73), so the
-    bound is the fp16 noise floor: the distance between the float64 graph and the oracle that rounds to
-    float16 at the storage points, x1.5 + 0.25 mm."""
+    """The whole CUDA path against the reference-code poses (the reference's own graph builders executed in float64,
+    oracle/gen_golden.py).  precision='strict' must reproduce them within BASELINE.json's 1e-3 mm; the tensor-core
+    path computes the backbone in float16 like the reference's default (src/options.py:73), so it is held to the
+    fp16 noise floor: the distance of the oracle that rounds to float16 at the storage points from the same vectors."""
     import torch
     from metro_pose3d_b200.inference import MetroModel
     g = np.load(os.path.join(GOLD, 'graph.npz'))
@@ -148,7 +148,13 @@ def test_cuda_graph_against_reference_code(name):
     w = synth_weights(spec, seed=wseed)
     img = synth_images(n, seed=iseed, side=side)
     want = g[f'{name}_poses']
+    x = torch.from_numpy(img).cuda()
+    strict = MetroModel(_arch(name), stride, 'h36m', weights=w, max_batch=n, precision='strict')
+    err = np.abs(strict.infer(x).cpu().numpy() - want).max()
+    assert err <= 1e-3, f'|strict - reference code| = {err:.3e} mm'
+    strict.close()
     model = MetroModel(_arch(name), stride, 'h36m', weights=w, max_batch=n)
-    got = model.infer(torch.from_numpy(img).cuda()).cpu().numpy()
-    noise = np.abs(OracleNet(spec, w, export_permutation('h36m'), 'half')(img) - want).max()
-    assert np.abs(got - want).max() < 1.5 * noise + 0.25, (np.abs(got - want).max(), noise)
+    got = model.infer(x).cpu().numpy()
+    noise = np.abs(OracleNet(spec, w, export_permutation('h36m'), 'half')(img) - want)
+    assert np.abs(got - want).mean() < 2.0 * noise.mean() + 0.05, (np.abs(got - want).mean(), noise.mean())
+    assert np.abs(got - want).max() < 3.0 * noise.max() + 0.25, (np.abs(got - want).max(), noise.max())

@@ -9,14 +9,15 @@ from oracle.metro_oracle import OracleNet
 
 pytestmark = pytest.mark.gpu
 
-# End-to-end tolerances.  The reference computes the backbone in float16 (src/options.py:73), so its
-# output is only defined up to the summation order of its fp16 convolutions: the oracle that rounds to
-# fp16 at the same storage points ('half' mode) and the CUDA path differ wherever fp32-vs-exact
-# accumulation flips an individual fp16 rounding, and those flips random-walk through ~50 layers.  The
-# e2e bound is therefore stated against the fp16 noise floor itself: |cuda - fp64| and |cuda - half|
-# must stay within 1.5x (+0.25 mm) of |half - fp64|, the distance between two legitimate evaluations
-# of the same fp16 graph.  The strict 1e-3 mm bound of BASELINE.json applies to the decode on
-# identical logits (checked below on the path's own head tensor and in tests/test_softargmax_gpu.py).
+# End-to-end tolerances (BASELINE.json: 1e-3 mm per joint against the reference graph).
+#   * precision='strict' (float64 on CUDA cores) meets 1e-3 mm against the float64 oracle on every config:
+#     tests/test_parity_gpu.py.
+#   * the tensor-core path is the reference's DEFAULT float16 graph (src/options.py:73), whose output is only
+#     defined up to the summation order of its fp16 convolutions: the oracle that rounds to fp16 at the same
+#     storage points ('half' mode) and the CUDA path differ wherever fp32-vs-exact accumulation flips an
+#     individual fp16 rounding, and those flips random-walk through ~50 layers.  Here it is checked layer by layer
+#     (relative L2 per tensor) and, for the decode, at 1e-3 mm on identical logits; its end-to-end distance from the
+#     float64 graph is gated statistically over 32 crops per config in tests/test_parity_gpu.py.
 LAYER_REL = 2e-3
 DECODE_TOL_MM = 1e-3
 
@@ -27,7 +28,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize('arch,stride,ds,n', [('resnet_v2_50', 32, 'h36m', 2), ('resnet_v2_50', 16, 'h36m', 2),
                                              ('resnet_v2_101', 16, 'coco19', 1), ('resnet_v2_50', 8, 'coco19', 1),
-                                             ('resnet_v2_50', 4, 'coco19', 1)])
+                                             ('resnet_v2_50', 4, 'coco19', 1), ('resnet_v2_101', 4, 'coco19', 1)])
 def test_layerwise_and_end_to_end(arch, stride, ds, n):
     import torch
     from metro_pose3d_b200.inference import MetroModel, estimate_pose
@@ -60,13 +61,9 @@ def test_layerwise_and_end_to_end(arch, stride, ds, n):
     # strict: the decode of the path's own head tensor
     strict = np.abs(poses - ora.decode(got_head)).max()
     assert strict < DECODE_TOL_MM, f'decode on identical logits: max |err| = {strict:.3e} mm'
-    # end to end against the fp16 noise floor
-    p64 = OracleNet(spec, w, perm, 'fp64')(img)
-    noise = np.abs(ref - p64).max()
-    bound = 1.5 * noise + 0.25
-    err_half, err64 = np.abs(poses - ref).max(), np.abs(poses - p64).max()
-    assert err_half < bound and err64 < bound, \
-        f'end-to-end: |cuda-half| {err_half:.3f} mm, |cuda-fp64| {err64:.3f} mm, fp16 noise floor {noise:.3f} mm'
+    # end to end: a coarse sanity bound here (1-2 crops); the statistical gate is tests/test_parity_gpu.py
+    err_half = np.abs(poses - ref).max()
+    assert err_half < 10.0, f'end-to-end: |cuda-half| {err_half:.3f} mm'
     assert poses.shape == (n, len(perm), 3) and len(names) == len(perm)
     if ds == 'h36m':
         assert np.all(poses[:, 0] == 0) and edges.shape == (16, 2) and names[0] == 'pelv'
@@ -91,7 +88,13 @@ def test_host_buffer_call_and_batch_invariance():
     with pytest.raises(ValueError):
         model.infer_host(img[:, :128])
     with pytest.raises(ValueError):
-        model.infer_host(np.zeros((9, 256, 256, 3), np.float32))      # > max_batch
+        model.infer_host(img, out=np.zeros((4, 17, 3), np.float32))   # undersized output buffer
+    # the graph's placeholder is [None,256,256,3]: batches above max_batch run in pieces of max_batch crops
+    big = synth_images(19, seed=1002)
+    e = model.infer_host(big)
+    f = np.concatenate([model.infer_host(big[:8]), model.infer_host(big[8:16]), model.infer_host(big[16:])])
+    assert np.array_equal(e, f)
+    assert np.array_equal(model.infer(torch.from_numpy(big).cuda()).cpu().numpy(), e)
 
 
 def test_sliced_host_path_equals_device_path():
@@ -159,14 +162,28 @@ def test_frozen_graph_import_runs_the_same_model(tmp_path):
     assert names == list(ji.names) and np.array_equal(edges, np.asarray(ji.edges))
 
 
-def test_uint8_ingestion_matches_float_path():
+def test_uint8_ingestion_is_bit_identical_to_the_float_path():
+    """uint8 crops (fused x * (1/255f), csrc/root_fused.cu) against float32 crops prepared exactly as the reference
+    does (np.float32(im) / 255, src/improc.py:56-61): after the cast to float16 (architectures.py:29) the two agree
+    for all 256 byte values, so conv1 and the poses must be bit-identical.  The first crop holds every byte value in
+    every channel."""
     import torch
     from metro_pose3d_b200.inference import MetroModel
-    model = MetroModel('resnet_v2_50', 32, 'h36m', max_batch=2)
-    u8 = torch.randint(0, 256, (2, 256, 256, 3), dtype=torch.uint8, device='cuda')
-    a = model.infer(u8)
-    b = model.infer(u8.float() / 255.0)
-    assert (a - b).abs().max().item() < 0.5
+    model = MetroModel('resnet_v2_50', 32, 'h36m', max_batch=2, keep_activations=True)
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 256, (2, 256, 256, 3), dtype=np.uint8)
+    u8[0] = (np.arange(256 * 256 * 3, dtype=np.int64).reshape(256, 256, 3) % 256).astype(np.uint8)
+    assert all(len(np.unique(u8[0, :, :, c])) == 256 for c in range(3))
+    f32 = u8.astype(np.float32) / np.float32(255)          # improc.normalize01
+    a = model.infer(torch.from_numpy(u8).cuda()).cpu().numpy()
+    conv1_a = model.debug_read('conv1').copy()
+    b = model.infer(torch.from_numpy(f32).cuda()).cpu().numpy()
+    conv1_b = model.debug_read('conv1')
+    assert np.array_equal(conv1_a, conv1_b)
+    assert np.array_equal(a, b)
+    # and the cast itself, exhaustively: fp16(k * (1/255f)) == fp16(float32(k) / 255)
+    k = np.arange(256, dtype=np.float32)
+    assert np.array_equal((k * np.float32(1.0 / 255.0)).astype(np.float16), (k / np.float32(255)).astype(np.float16))
 
 
 def test_uint8_host_path_equals_device_path():
