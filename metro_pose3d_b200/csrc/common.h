@@ -57,6 +57,9 @@ struct SoftargmaxLaunch {
   int tpj;                 // threads per joint in the merge (power of two <= 32)
   long long *prof;         // debug (METRO_SAM_PROF): 8 clock64 stamps per CTA, or null
   int head_f16;
+  // dataflow (ptx.cuh): wait for the crop's counter of the logits layer instead of for the whole previous grid
+  const unsigned int *dep_flags;   // indexed by crop of THIS launch (already offset), or null
+  unsigned int dep_expected;
 };
 metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLaunch &L);
 size_t softargmax_workspace_bytes(const SoftargmaxLaunch &L);

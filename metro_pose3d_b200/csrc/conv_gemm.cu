@@ -152,8 +152,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
   const uint32_t tmem_base = *s_tmem;
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) ran while the
   // previous kernel in the stream was still draining; its outputs may only be touched from here on.
-  ptx::griddep_wait();
+  // (With dataflow counters the grid-wide wait is replaced by per-crop waits in the activation producer: this kernel's
+  // first tiles start while the previous layer's last wave is still running.)
+  if (!p.dep_flags) ptx::griddep_wait();
   ptx::griddep_launch_dependents();
+  const int n_end = p.m_total / (p.ho * p.wo);       // one past the last crop of this call's slice
 
   if (warp == 0 || warp == 3) {
     // ================================ TMA producers ===============================
@@ -207,6 +210,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
         const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
         left = k0 + n2;
         id_blocks = p.diag2 ? n2 : 0;
+        if (is_a && p.dep_flags) {
+          // the crops this CTA's 128 pixels belong to must be complete in the producer layer (its inputs from
+          // earlier layers are then complete too: every layer waited for the same crops of its own producer)
+          const int c_end = min(n0 + p.nb, n_end);
+          for (int c = n0; c < c_end; ++c) ptx::flag_wait(p.dep_flags + c, p.dep_expected);
+          ptx::fence_proxy_async_all();
+        }
         if (p.tall) {
           // 3x3 stride-1 convolution, "tall" staging: a stage holds, for one kernel column kw and one channel
           // block, the (th + 2*rate) input rows that serve all three kernel rows (one column-shifted box; TMA
@@ -426,6 +436,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
     const uint32_t row_a = uint32_t(lane) * 64u, sw = uint32_t(lane >> 1) & 3u;
     const uint32_t tempty0 = ptx::mapa(ptx::smem_u32(tempty + g), 0);   // the leader's barrier
     int cur_nt = -1;
+    unsigned int *sig_prev = nullptr;                // counter of the tile whose stores are still in flight
     long long t_acc = 0, t_busy = 0, t_store = 0, t_ld = 0, t_math = 0, t_sts = 0, t_issue = 0, t_par = 0;
     uint32_t k = 0;
     for (int tile = pair + g * n_pairs; tile < n_tiles_total; tile += 2 * n_pairs, ++k) {
@@ -497,8 +508,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
           }
         }
         ptx::tc_fence_before();
+        if (p.sig_flags) __threadfence();            // this lane's stores, GPU scope, before the warp's report
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(tempty0);
+        if (lane == 0) {
+          ptx::mbar_arrive_cluster(tempty0);
+          if (p.sig_flags && m0 < p.m_total) ptx::flag_signal(p.sig_flags + m0 / (p.ho * p.wo));
+        }
       } else {
         // ---- fp16 path: TMEM -> registers -> swizzled 32x32 box in smem -> TMA store.
         //      (The identity-shortcut residual is not an epilogue operand: it is accumulated by the
@@ -582,10 +597,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
             t_ld += c1 - c0; t_math += c2 - c1; t_store += c3 - c2; t_sts += c4 - c3; t_issue += clock64() - c4;
           }
         }
+        if (p.sig_flags && lane == 0) {
+          // report the PREVIOUS tile's rows: its kChunks store groups are complete once at most the kChunks groups
+          // of this tile are still pending (no wait in practice: they were issued a whole tile ago)
+          if (sig_prev) {
+            ptx::bulk_wait<kChunks>();
+            ptx::fence_proxy_async_all();
+            ptx::flag_signal(sig_prev);
+          }
+          sig_prev = m0 < p.m_total ? p.sig_flags + m0 / (p.ho * p.wo) : nullptr;
+        }
       }
       if (prof) t_busy += clock64() - t1;
     }
-    if (kMode != kDirect && lane == 0) ptx::bulk_wait<0>();    // smem must outlive the last TMA store
+    if (kMode != kDirect && lane == 0) {
+      ptx::bulk_wait<0>();                                     // smem must outlive the last TMA store
+      if (sig_prev) { ptx::fence_proxy_async_all(); ptx::flag_signal(sig_prev); }
+    }
     if (prof && e == 0 && lane == 0) {
       p.prof[blockIdx.x * kPCount + kPEpiWaitAcc] = t_acc;
       p.prof[blockIdx.x * kPCount + kPEpiBusy] = t_busy;

@@ -50,6 +50,12 @@ struct alignas(64) ConvGemmParams {
   int stages;
   int off_stage, off_par, off_apar, off_bar, smem_bytes;
   long long *prof;       // optional [grid][8] per-CTA role timers (cycles); nullptr = off
+  // cross-kernel dataflow (ptx.cuh): instead of waiting for the whole previous grid (griddepcontrol.wait) a tile
+  // waits until the PRODUCER layer has completed the crops it reads, and every epilogue warp reports its 32 rows
+  // of a crop once their stores are complete.  Counters are indexed by absolute crop; null = off.
+  const unsigned int *dep_flags;   // producer layer's counters
+  unsigned int dep_expected;       // pieces per crop the producer reports: (its output pixels per crop / 32) x its N tiles
+  unsigned int *sig_flags;         // this layer's counters
 };
 
 struct ConvGemmLaunch {
@@ -58,6 +64,7 @@ struct ConvGemmLaunch {
   bool direct = false;     // direct-store epilogue (logits head: cout not a multiple of 64)
   std::string name;
   double flops_per_img = 0;
+  unsigned int sig_expected = 0;   // what this layer's counters reach per crop: (ho * wo / 32) x n_tiles
 };
 
 // Tensor-map helpers (driver entry point resolved at run time; no link-time libcuda dependency).

@@ -194,6 +194,7 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
     if ((st = conv_gemm_plan_smem(L, kb_tile)) != METRO_OK) return st;
   }
   L.flops_per_img = 2.0 * g.out_side * g.out_side * double(g.cout) * K;
+  L.sig_expected = unsigned(g.out_side * g.out_side / 32) * unsigned(p.n_tiles);   // one report per epilogue warp (32 rows) and N tile
   conv_gemm_set_batch(p, g.n_max);
   return METRO_OK;
 }
@@ -227,6 +228,8 @@ struct metro_handle {
   std::string joint_names;       // the graph's constant fetches (main.py:128,140-141), '\n'-separated
   std::vector<int32_t> joint_edges;
   size_t weight_bytes = 0;       // part of arena.total that does not scale with max_batch
+  unsigned int *flags = nullptr; // dataflow counters [1 + gemms][max_batch]: row 0 = fused root, row 1 + i = gemms[i]
+  int dataflow = 1;              // METRO_NO_DATAFLOW switches back to grid-wide dependencies (griddepcontrol.wait)
   int stem_chunk = 0;            // METRO_STEM_CHUNK: metro_infer runs the stem in slices of this many crops (0 = whole batch)
   int alternate = 1;      // consecutive convolutions walk their tile lists in opposite directions (METRO_NO_ALTERNATE)
   int host_chunk = 64;    // crops per PCIe slice of metro_infer_host (METRO_HOST_CHUNK)
@@ -434,6 +437,15 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     METRO_CUDA(cudaMemset(h.sam_ws, 0, ws));
   }
   h.weight_bytes = A.uploaded;
+  if (getenv("METRO_NO_DATAFLOW")) h.dataflow = 0;
+  if (keep) h.dataflow = 0;      // debug handles keep grid-wide dependencies
+  {
+    void *q = nullptr;
+    const size_t fb = (h.gemms.size() + 1) * size_t(N) * sizeof(unsigned int);
+    if ((st = A.alloc(&q, fb)) != METRO_OK) return st;
+    METRO_CUDA(cudaMemset(q, 0, fb));
+    h.flags = static_cast<unsigned int *>(q);
+  }
   METRO_CUDA(cudaDeviceSynchronize());
   return METRO_OK;
 }
@@ -443,6 +455,16 @@ struct Timer {
   std::vector<std::string> names;
   long long *role_prof = nullptr;   // device [launch][num_sms][8] role timers (METRO_ROLE_PROF=1)
 };
+
+// Dataflow wiring of convolution `li`: it waits on the counters of its producer (row li: the fused root for li == 0,
+// else gemms[li - 1]) and reports into row li + 1.
+void set_dataflow(const metro_handle *h, int li, ConvGemmParams &prm) {
+  if (!h->dataflow) return;
+  const size_t N = size_t(h->max_batch);
+  prm.dep_flags = h->flags + size_t(li) * N;
+  prm.dep_expected = li == 0 ? kRootBandsPerCrop : h->gemms[li - 1].sig_expected;
+  prm.sig_flags = h->flags + size_t(li + 1) * N;
+}
 
 // Launches the stem (space-to-depth pack, conv1, pool1 and the first `stem_gemms` tensor-core
 // convolutions) for crops [n_base, n_base + n) of the handle's buffers; `images` points at crop n_base.
@@ -460,7 +482,7 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
   mark("img_pack");
   if ((st = root_fused_launch(h->image_map, h->d_root_w, h->d_root_bias, h->d_pool_scale, h->d_pool_shift,
                               h->spec.keep_activations ? h->pool_raw : nullptr, h->pool_pre, h->buf_root, n, n_base, h->num_sms, s,
-                              (t && t->role_prof) ? t->role_prof : nullptr)) != METRO_OK) return st;
+                              (t && t->role_prof) ? t->role_prof : nullptr, h->dataflow ? h->flags : nullptr)) != METRO_OK) return st;
   mark("conv1+pool1");
   for (int li = 0; li < stem_gemms; ++li) {
     // the handle's launch record is never written after metro_create: the batch slice, walk direction and
@@ -471,6 +493,7 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
     conv_gemm_set_batch(prm, n, n_base);
     prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;     // the root kernel walks forwards
     prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
+    set_dataflow(h, li, prm);
     if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
@@ -492,10 +515,15 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
     conv_gemm_set_batch(prm, n, n_base);
     prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;
     prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
+    set_dataflow(h, int(li), prm);
     if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
   SoftargmaxLaunch sl = h->sam;
+  if (h->dataflow) {
+    sl.dep_flags = h->flags + h->gemms.size() * size_t(h->max_batch) + n_base;
+    sl.dep_expected = h->gemms.back().sig_expected;
+  }
   const size_t head_bytes = size_t(sl.H) * sl.W * sl.C * (sl.head_f16 ? 2 : 4);
   sl.n = n;
   sl.head = static_cast<const unsigned char *>(h->buf_head) + size_t(n_base) * head_bytes;
@@ -520,6 +548,8 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
     t->ev.push_back(e); t->names.push_back("start");
   }
   if (h->strict) return strict_run(h->strict, images, u8, n, poses, s);
+  if (h->dataflow)     // every crop of this call is produced once per layer: its counters start from zero
+    METRO_CUDA(cudaMemsetAsync(h->flags, 0, (h->gemms.size() + 1) * size_t(h->max_batch) * sizeof(unsigned int), s));
   if (h->stem_chunk > 0 && h->stem_chunk < n && !t) {
     // experiment knob: the stem (maps of 32x32 and larger, HBM-bound) in slices small enough for a layer's
     // output to still sit in L2 when the next layer reads it; the deep blocks once on the whole batch
@@ -728,6 +758,8 @@ metro_status infer_host(metro_handle *h, const void *images_host_v, bool u8, int
     marks.emplace_back(what, e);
   };
   if (trace) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_stream); }
+  if (h->dataflow)
+    METRO_CUDA(cudaMemsetAsync(h->flags, 0, (h->gemms.size() + 1) * size_t(h->max_batch) * sizeof(unsigned int), h->stream));
   mark("start", h->copy_stream);
   for (int lo = 0; lo < n; lo += chunk, ++i) {
     const int cnt = lo + chunk <= n ? chunk : n - lo;

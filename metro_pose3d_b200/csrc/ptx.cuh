@@ -237,6 +237,8 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // 64-bit store into the shared memory of another CTA of the cluster (address from mapa)
 __device__ __forceinline__ void st_cluster_f64(uint32_t cluster_addr, double v) {
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
@@ -304,6 +306,33 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t cta_mas
 // launch_dependents: lets the next grid in the stream start launching (its CTAs then sit in their own wait)
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- cross-kernel dataflow: per-crop completion counters in global memory --------------------------------
+// A producer layer adds 1 to its crop's counter after the stores of a piece of that crop are complete (release, GPU
+// scope); a consumer spins (acquire) until the counter reaches the number of pieces.  The data itself moves through the
+// async proxy (TMA stores / loads), the counter through the generic proxy: a proxy fence on both sides orders them.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void flag_signal(unsigned int *flag) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+}
+__device__ __forceinline__ unsigned int flag_load(const unsigned int *flag) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  return v;
+}
+// Bounded like mbar_wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void flag_wait(const unsigned int *flag, unsigned int expected) {
+  if (flag_load(flag) >= expected) return;
+  const long long t0 = clock64();
+  while (flag_load(flag) < expected) {
+    __nanosleep(100);
+    if (clock64() - t0 > (1ll << 31)) {
+      printf("metro: dataflow wait timed out (block %d thread %d: counter %u of %u)\n", int(blockIdx.x), int(threadIdx.x),
+             flag_load(flag), expected);
+      __trap();
+    }
+  }
+}
 
 // ---- misc ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long globaltimer() {

@@ -53,6 +53,7 @@ struct alignas(64) RootParams {
   __half *conv_dbg;        // optional [n][128][128][64]: conv1 output (keep_activations)
   int n, n_base, bands_per_img, pool_rows_per_band;   // crops n_base .. n_base + n of the buffers
   long long *prof;         // optional [grid][16] role timers (cycles)
+  unsigned int *sig_flags; // optional per-crop completion counters (ptx.cuh dataflow): +1 per finished band
 };
 
 constexpr int kOffW = kStages * kStageBytes;                 // 61440
@@ -306,6 +307,12 @@ __global__ void __launch_bounds__(kThreads, 1) root_fused_kernel(const __grid_co
           *reinterpret_cast<uint4 *>(p.pre + o) = po;
         }
       }
+      if (p.sig_flags) {
+        // this band's pooled rows are stored: every thread publishes its stores (GPU scope), one reports the band
+        __threadfence();
+        ptx::named_bar_sync(1, 256);
+        if (et == 0) ptx::flag_signal(p.sig_flags + img);
+      }
     }
     if (p.prof && e == 0 && lane == 0) { p.prof[blockIdx.x * 16 + 6] = clock64() - t_epi_start; p.prof[blockIdx.x * 16 + 7] = t_epi_wait; }
   }
@@ -407,7 +414,7 @@ metro_status img_pack_launch(const void *img, bool u8, __half *out, int n, cudaS
 
 metro_status root_fused_launch(const void *image_map, const __half *wpack, const float *bias, const float *pscale,
                                const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base,
-                               int num_sms, cudaStream_t stream, long long *prof) {
+                               int num_sms, cudaStream_t stream, long long *prof, unsigned int *sig_flags) {
   if (n == 0) return METRO_OK;
   static PerDeviceOnce configured;     // function attributes are per device
   metro_status cst = configured.run([] {
@@ -419,7 +426,7 @@ metro_status root_fused_launch(const void *image_map, const __half *wpack, const
   p.pmap = *static_cast<const CUtensorMap *>(image_map);
   p.wpack = wpack; p.bias = bias; p.pscale = pscale; p.pshift = pshift;
   p.raw = raw; p.pre = pre; p.conv_dbg = conv_dbg;
-  p.prof = prof;
+  p.prof = prof; p.sig_flags = sig_flags;
   p.n = n; p.n_base = n_base; p.pool_rows_per_band = 8; p.bands_per_img = kPoolW / 8;
   const int n_bands = n * p.bands_per_img;
   cudaLaunchConfig_t cfg = {};

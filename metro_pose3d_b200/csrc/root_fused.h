@@ -16,5 +16,7 @@ metro_status img_pack_launch(const void *img, bool u8, __half *out, int n, cudaS
 // works on crops n_base .. n_base + n of all buffers
 metro_status root_fused_launch(const void *image_map, const __half *wpack, const float *bias, const float *pscale,
                                const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base,
-                               int num_sms, cudaStream_t stream, long long *prof = nullptr);
+                               int num_sms, cudaStream_t stream, long long *prof = nullptr,
+                               unsigned int *sig_flags = nullptr);
+constexpr unsigned int kRootBandsPerCrop = 8;   // what a crop's counter reaches when sig_flags is given
 }  // namespace metro

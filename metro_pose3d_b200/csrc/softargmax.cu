@@ -174,8 +174,18 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
   const bool prof = p.prof != nullptr && tid == 0;
   long long *stamp = p.prof + size_t(blockIdx.x) * 8;
   if (prof) { stamp[0] = clock64(); stamp[6] = (long long)ptx::globaltimer(); }
-  ptx::griddep_wait();
+  if (p.dep_flags) {
+    // one thread polls the crop's counter (acquire, GPU scope); the barrier extends the ordering to the CTA
+    if (tid == 0) ptx::flag_wait(p.dep_flags + img, p.dep_expected);
+    __syncthreads();
+  } else {
+    ptx::griddep_wait();
+  }
   ptx::griddep_launch_dependents();
+  // distributed shared memory of a peer may only be written once that CTA is known to have started: every CTA of a
+  // split crop arrives here and waits just before its remote stores (found by compute-sanitizer: "block that might
+  // not have entered yet"; in practice the whole stream lies in between)
+  if (p.cluster && p.splits > 1) ptx::cluster_arrive();
   if (prof) stamp[1] = clock64();
 
 #pragma unroll
@@ -259,6 +269,7 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
     }
   }
   __syncthreads();
+  if (p.cluster && p.splits > 1) ptx::cluster_wait();
   if (prof) stamp[3] = clock64();
   // a split crop's per-joint record goes to the first CTA of its cluster through distributed shared memory, or
   // -- when the launch has no clusters (split counts that are not 2, 4 or 8) -- to the global workspace

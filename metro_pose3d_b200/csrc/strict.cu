@@ -41,7 +41,9 @@ struct SConv {
 };
 
 __device__ __forceinline__ double quantize(double v, int quant) {
-  if (quant == 1) return double(__half2float(__double2half(v)));
+  // float64 -> float32 -> float16: the route of the tensor-core path (float32 accumulator, then cvt.rn.f16.f32) and
+  // of the oracle's 'half' mode (torch converts double to half through float)
+  if (quant == 1) return double(__half2float(__float2half_rn(float(v))));
   if (quant == 2) return double(float(v));
   return v;
 }
