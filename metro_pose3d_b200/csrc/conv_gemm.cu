@@ -174,6 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
       const uint32_t full0 = ptx::mapa(ptx::smem_u32(full), kXform ? rank : 0);
       int sub = 0, left = 0;                        // K block within the stage; K blocks of the tile still to load
       int id_blocks = 0;                            // identity K blocks at the end of the current tile
+      bool dep_all_done = false;                    // dataflow: the producer layer has been seen complete
       auto acquire = [&]() -> unsigned char * {
         if (sub == 0) {
           if (prof) {
@@ -210,11 +211,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
         const int n2 = p.diag2 ? min(BLOCK_N / 64, p.cblk1 - cb2_0) : p.cblk1;
         left = k0 + n2;
         id_blocks = p.diag2 ? n2 : 0;
-        if (is_a && p.dep_flags) {
+        if (is_a && p.dep_flags && !dep_all_done) {
           // the crops this CTA's 128 pixels belong to must be complete in the producer layer (its inputs from
           // earlier layers are then complete too: every layer waited for the same crops of its own producer)
-          const int c_end = min(n0 + p.nb, n_end);
-          for (int c = n0; c < c_end; ++c) ptx::flag_wait(p.dep_flags + c, p.dep_expected);
+          if (ptx::flag_load(p.dep_done) >= p.dep_ctas) {
+            dep_all_done = true;                     // the whole producer grid has exited: no more polling
+          } else {
+            const int c_end = min(n0 + p.nb, n_end);
+            for (int c = n0; c < c_end; ++c) ptx::flag_wait(p.dep_flags + c, p.dep_expected);
+          }
           ptx::fence_proxy_async_all();
         }
         if (p.tall) {
@@ -633,6 +638,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
     ptx::tc_fence_after();
     ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
   }
+  if (p.sig_done && threadIdx.x == 0) {              // every warp of this CTA has passed its final store wait
+    ptx::fence_proxy_async_all();
+    ptx::flag_signal(p.sig_done);
+  }
   if (prof && threadIdx.x == 0) p.prof[blockIdx.x * kPCount + kPTotal] = clock64() - t_start;
 }
 
@@ -653,6 +662,12 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+int grid_for(const ConvGemmParams &prm, int num_sms) {
+  const int pair_tiles = ((prm.m_tiles + 1) / 2) * prm.n_tiles;
+  const int max_pairs = num_sms / 2;
+  return 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // CTA pairs (cluster of 2)
+}
+
 template <int BLOCK_N, int kMode, bool kXform = false>
 metro_status launch_t(const ConvGemmParams &prm, int num_sms, cudaStream_t stream) {
   // function attributes are per device: one opt-in per (instantiation, device), safe across threads
@@ -665,8 +680,7 @@ metro_status launch_t(const ConvGemmParams &prm, int num_sms, cudaStream_t strea
   if (cst != METRO_OK) return cst;
   const int pair_tiles = ((prm.m_tiles + 1) / 2) * prm.n_tiles;
   if (pair_tiles == 0) return METRO_OK;
-  const int max_pairs = num_sms / 2;
-  const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // CTA pairs (cluster of 2)
+  const int grid = grid_for(prm, num_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kXform ? kThreadsXform : kThreads);
   cfg.dynamicSmemBytes = size_t(prm.smem_bytes); cfg.stream = stream;
@@ -680,6 +694,8 @@ metro_status launch_t(const ConvGemmParams &prm, int num_sms, cudaStream_t strea
 }
 
 }  // namespace
+
+int conv_gemm_grid(const ConvGemmParams &prm, int num_sms) { return grid_for(prm, num_sms); }
 
 metro_status make_out_tensor_map(CUtensorMap *map, const void *base, long long m_rows, int cout) {
   EncodeTiledFn fn = encode_fn();

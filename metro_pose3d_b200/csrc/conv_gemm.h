@@ -56,6 +56,11 @@ struct alignas(64) ConvGemmParams {
   const unsigned int *dep_flags;   // producer layer's counters
   unsigned int dep_expected;       // pieces per crop the producer reports: (its output pixels per crop / 32) x its N tiles
   unsigned int *sig_flags;         // this layer's counters
+  // whole-layer shortcut: every CTA adds 1 to its layer's word on exit; once a consumer has seen the producer's word
+  // reach the producer's grid size it stops polling per-crop counters (the steady state of a launch)
+  const unsigned int *dep_done;
+  unsigned int dep_ctas;
+  unsigned int *sig_done;
 };
 
 struct ConvGemmLaunch {
@@ -65,6 +70,7 @@ struct ConvGemmLaunch {
   std::string name;
   double flops_per_img = 0;
   unsigned int sig_expected = 0;   // what this layer's counters reach per crop: (ho * wo / 32) x n_tiles
+  bool signals = false;            // long tiles (a whole crop or more per CTA tile): worth a report per tile
 };
 
 // Tensor-map helpers (driver entry point resolved at run time; no link-time libcuda dependency).
@@ -83,6 +89,8 @@ metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side);
 // `prm` = L.prm with this call's batch slice / direction / profiling pointer filled in (L itself is never mutated
 // after it is built, so launches are capture-safe).
 metro_status conv_gemm_launch(const ConvGemmLaunch &L, const ConvGemmParams &prm, int num_sms, cudaStream_t stream);
+// CTAs the launch of `prm` runs (what its sig_done word reaches)
+int conv_gemm_grid(const ConvGemmParams &prm, int num_sms);
 // Packs HWIO float32 filters into [cout_pad][K] fp16 in the kernel's K-block order; `w2` (1x1,
 // [cin2][cout]) is appended along K.
 void conv_gemm_pack_weights(const float *w_hwio, int k, int cin, int cout, const float *w2, int cin2,

@@ -195,6 +195,10 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   }
   L.flops_per_img = 2.0 * g.out_side * g.out_side * double(g.cout) * K;
   L.sig_expected = unsigned(g.out_side * g.out_side / 32) * unsigned(p.n_tiles);   // one report per epilogue warp (32 rows) and N tile
+  // Reports cost a GPU-scope release per epilogue warp and tile: affordable where a CTA tile is a whole crop or more
+  // (maps of 16x16 and below: tiles of 5-50 us), not for the ~2 us tiles of the 64x64 / 32x32 layers (measured: +9 %
+  // on the step with every layer reporting)
+  L.signals = g.out_side * g.out_side <= 2 * kTileM;
   conv_gemm_set_batch(p, g.n_max);
   return METRO_OK;
 }
@@ -229,6 +233,7 @@ struct metro_handle {
   std::vector<int32_t> joint_edges;
   size_t weight_bytes = 0;       // part of arena.total that does not scale with max_batch
   unsigned int *flags = nullptr; // dataflow counters [1 + gemms][max_batch]: row 0 = fused root, row 1 + i = gemms[i]
+  std::vector<unsigned int> df_launched;   // per layer: CTAs launched since the counters were last zeroed (this call)
   int dataflow = 1;              // METRO_NO_DATAFLOW switches back to grid-wide dependencies (griddepcontrol.wait)
   int stem_chunk = 0;            // METRO_STEM_CHUNK: metro_infer runs the stem in slices of this many crops (0 = whole batch)
   int alternate = 1;      // consecutive convolutions walk their tile lists in opposite directions (METRO_NO_ALTERNATE)
@@ -441,7 +446,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
   if (keep) h.dataflow = 0;      // debug handles keep grid-wide dependencies
   {
     void *q = nullptr;
-    const size_t fb = (h.gemms.size() + 1) * size_t(N) * sizeof(unsigned int);
+    const size_t fb = ((h.gemms.size() + 1) * size_t(N) + h.gemms.size() + 1) * sizeof(unsigned int);   // + a word per layer
     if ((st = A.alloc(&q, fb)) != METRO_OK) return st;
     METRO_CUDA(cudaMemset(q, 0, fb));
     h.flags = static_cast<unsigned int *>(q);
@@ -458,12 +463,33 @@ struct Timer {
 
 // Dataflow wiring of convolution `li`: it waits on the counters of its producer (row li: the fused root for li == 0,
 // else gemms[li - 1]) and reports into row li + 1.
-void set_dataflow(const metro_handle *h, int li, ConvGemmParams &prm) {
+// Only layers with long tiles report (ConvGemmLaunch::signals); a layer whose producer does not report keeps the
+// grid-wide dependency.  `n` / `n_base`: this call's slice (the producer ran on the same slice).
+void set_dataflow(metro_handle *h, int li, ConvGemmParams &prm) {
   if (!h->dataflow) return;
   const size_t N = size_t(h->max_batch);
-  prm.dep_flags = h->flags + size_t(li) * N;
-  prm.dep_expected = li == 0 ? kRootBandsPerCrop : h->gemms[li - 1].sig_expected;
-  prm.sig_flags = h->flags + size_t(li + 1) * N;
+  unsigned int *done = h->flags + (h->gemms.size() + 1) * N;     // one word per layer after the per-crop rows
+  if (li > 0 && h->gemms[li - 1].signals) {
+    prm.dep_flags = h->flags + size_t(li) * N;
+    prm.dep_expected = h->gemms[li - 1].sig_expected;
+    // "the producer layer is complete" = every CTA it has launched so far in this call has exited (a call may run a
+    // layer in several slices; all of them precede this launch in the stream)
+    prm.dep_done = done + li;
+    prm.dep_ctas = h->df_launched[li];
+  }
+  if (h->gemms[li].signals) {
+    prm.sig_flags = h->flags + size_t(li + 1) * N;
+    prm.sig_done = done + li + 1;
+    h->df_launched[li + 1] += unsigned(conv_gemm_grid(prm, h->num_sms));
+  }
+}
+
+// zeroes the dataflow counters at the start of a call (every crop of a call is produced once per layer)
+metro_status reset_dataflow(metro_handle *h, cudaStream_t s) {
+  if (!h->dataflow) return METRO_OK;
+  h->df_launched.assign(h->gemms.size() + 1, 0u);
+  METRO_CUDA(cudaMemsetAsync(h->flags, 0, ((h->gemms.size() + 1) * size_t(h->max_batch) + h->gemms.size() + 1) * sizeof(unsigned int), s));
+  return METRO_OK;
 }
 
 // Launches the stem (space-to-depth pack, conv1, pool1 and the first `stem_gemms` tensor-core
@@ -482,7 +508,7 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
   mark("img_pack");
   if ((st = root_fused_launch(h->image_map, h->d_root_w, h->d_root_bias, h->d_pool_scale, h->d_pool_shift,
                               h->spec.keep_activations ? h->pool_raw : nullptr, h->pool_pre, h->buf_root, n, n_base, h->num_sms, s,
-                              (t && t->role_prof) ? t->role_prof : nullptr, h->dataflow ? h->flags : nullptr)) != METRO_OK) return st;
+                              (t && t->role_prof) ? t->role_prof : nullptr, nullptr)) != METRO_OK) return st;
   mark("conv1+pool1");
   for (int li = 0; li < stem_gemms; ++li) {
     // the handle's launch record is never written after metro_create: the batch slice, walk direction and
@@ -520,7 +546,7 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
     mark(L.name.c_str());
   }
   SoftargmaxLaunch sl = h->sam;
-  if (h->dataflow) {
+  if (h->dataflow && h->gemms.back().signals) {
     sl.dep_flags = h->flags + h->gemms.size() * size_t(h->max_batch) + n_base;
     sl.dep_expected = h->gemms.back().sig_expected;
   }
@@ -548,8 +574,10 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
     t->ev.push_back(e); t->names.push_back("start");
   }
   if (h->strict) return strict_run(h->strict, images, u8, n, poses, s);
-  if (h->dataflow)     // every crop of this call is produced once per layer: its counters start from zero
-    METRO_CUDA(cudaMemsetAsync(h->flags, 0, (h->gemms.size() + 1) * size_t(h->max_batch) * sizeof(unsigned int), s));
+  {
+    metro_status rst = reset_dataflow(h, s);
+    if (rst != METRO_OK) return rst;
+  }
   if (h->stem_chunk > 0 && h->stem_chunk < n && !t) {
     // experiment knob: the stem (maps of 32x32 and larger, HBM-bound) in slices small enough for a layer's
     // output to still sit in L2 when the next layer reads it; the deep blocks once on the whole batch
@@ -758,8 +786,10 @@ metro_status infer_host(metro_handle *h, const void *images_host_v, bool u8, int
     marks.emplace_back(what, e);
   };
   if (trace) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_stream); }
-  if (h->dataflow)
-    METRO_CUDA(cudaMemsetAsync(h->flags, 0, (h->gemms.size() + 1) * size_t(h->max_batch) * sizeof(unsigned int), h->stream));
+  {
+    metro_status rst = reset_dataflow(h, h->stream);
+    if (rst != METRO_OK) return rst;
+  }
   mark("start", h->copy_stream);
   for (int lo = 0; lo < n; lo += chunk, ++i) {
     const int cnt = lo + chunk <= n ? chunk : n - lo;

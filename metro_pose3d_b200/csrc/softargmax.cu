@@ -174,6 +174,16 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
   const bool prof = p.prof != nullptr && tid == 0;
   long long *stamp = p.prof + size_t(blockIdx.x) * 8;
   if (prof) { stamp[0] = clock64(); stamp[6] = (long long)ptx::globaltimer(); }
+  if (!p.dep_flags && p.l2_prefetch) {
+    // Ahead of the dependency wait the item's bytes are pulled from HBM into L2 (a prefetch reads no values, so it is
+    // safe whatever the previous kernel is still writing: L2 is the point of coherence).  In a stream of launches
+    // this overlaps the HBM transfer of launch k+1 with the merge / output tail and the completion latency of launch
+    // k, during which the memory system would otherwise idle (~2 us of every ~10 at 256 crops).
+    const unsigned char *b0 = static_cast<const unsigned char *>(p.head) + (size_t(img) * P + px0) * C * esize;
+    const int bytes = (px1 - px0) * C * esize;
+    for (int off = tid * 128; off < bytes; off += int(blockDim.x) * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
+  }
   if (p.dep_flags) {
     // one thread polls the crop's counter (acquire, GPU scope); the barrier extends the ordering to the CTA
     if (tid == 0) ptx::flag_wait(p.dep_flags + img, p.dep_expected);
@@ -602,6 +612,7 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   L.splits = (P + L.ipx - 1) / L.ipx;              // no empty item
   // 2, 4 or 8 CTAs per crop run as one thread-block cluster and merge through distributed shared memory
   L.cluster = (L.splits == 2 || L.splits == 4 || L.splits == 8) && !getenv("METRO_SAM_NO_CLUSTER") ? 1 : 0;
+  L.l2_prefetch = getenv("METRO_SAM_NO_PREFETCH") ? 0 : 1;
   if (smem_bytes(L) > 100 * 1024) return fail(METRO_ERR_VALUE, "softargmax: shared memory budget exceeded");
   return METRO_OK;
 }

@@ -29,7 +29,7 @@ pytestmark = pytest.mark.gpu
 STRICT_TOL_MM = 1e-3          # BASELINE.json north_star: "within 1e-3 mm per joint"
 # statistical gate of the float16 tensor-core path: its error distribution may not be wider than that of the ideal
 # float16 evaluation by more than these factors (32 crops x J x 3 samples, fixed seeds, deterministic kernels)
-MEAN_FACTOR, P99_FACTOR = 1.25, 1.35
+MEAN_FACTOR, P99_FACTOR = 1.1, 1.1      # measured on the five configs: 0.94-0.99 / 0.92-1.00 (profiles/r2_parity_table.json)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
