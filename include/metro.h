@@ -199,6 +199,13 @@ metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf,
 /* Per-launch device times (ms) of the last metro_profile call, one entry per kernel launch. */
 metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev,
                            float *ms_out, char *names_buf, size_t names_bytes, int32_t *n_launches);
+/* Small batches are launch-bound (52 launches of a few microseconds each for ResNet-50), so metro_infer /
+ * metro_infer_u8 capture a call's launch sequence into a CUDA graph the second time they see the same
+ * (n, dtype, image buffer, pose buffer) with n <= 32 (environment METRO_GRAPH_MAX_BATCH; 0 disables) and
+ * replay it afterwards -- the role the TensorFlow session's cached executor plays for the reference's
+ * sess.run (inference.py:25-27).  Up to 8 graphs per handle, least recently used evicted.  Reports the number
+ * of instantiated graphs and of replays so far. */
+metro_status metro_graph_stats(const metro_handle *h, int32_t *graphs, int64_t *replays);
 /* Number of kernel launches one metro_infer(n) enqueues. */
 metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launches);
 

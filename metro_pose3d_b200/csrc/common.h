@@ -58,6 +58,7 @@ struct SoftargmaxLaunch {
   long long *prof;         // debug (METRO_SAM_PROF): 8 clock64 stamps per CTA, or null
   int head_f16;
   int l2_prefetch;         // pull the item's bytes into L2 ahead of the dependency wait (stand-alone launches)
+  int early;               // CTAs [0, early) also prefetch an equal share of the whole input (they start early)
   // dataflow (ptx.cuh): wait for the crop's counter of the logits layer instead of for the whole previous grid
   const unsigned int *dep_flags;   // indexed by crop of THIS launch (already offset), or null
   unsigned int dep_expected;

@@ -233,7 +233,20 @@ struct metro_handle {
   std::vector<int32_t> joint_edges;
   size_t weight_bytes = 0;       // part of arena.total that does not scale with max_batch
   unsigned int *flags = nullptr; // dataflow counters [1 + gemms][max_batch]: row 0 = fused root, row 1 + i = gemms[i]
+  // CUDA-graph executor for small batches (launch-bound: 52 launches of a few microseconds each): the launch
+  // sequence of a call is captured once per (batch, dtype, buffers) and replayed
+  struct GraphEntry {
+    int n = 0; bool u8 = false; const void *images = nullptr; float *poses = nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    int seen = 0; bool failed = false; unsigned long long last_use = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  int graph_max_batch = 32;      // METRO_GRAPH_MAX_BATCH (0 = never capture)
+  unsigned long long graph_clock = 0, graph_replays = 0;
   std::vector<unsigned int> df_launched;   // per layer: CTAs launched since the counters were last zeroed (this call)
+  int df_forward = 1;            // METRO_DF_KEEP_ALTERNATE: dataflow layers keep the alternating tile order
+  int xform_max_cb = 256;        // METRO_XFORM_MAX_CB: widest bottleneck whose conv1 applies the pre-activation in-kernel
   int dataflow = 1;              // METRO_NO_DATAFLOW switches back to grid-wide dependencies (griddepcontrol.wait)
   int stem_chunk = 0;            // METRO_STEM_CHUNK: metro_infer runs the stem in slices of this many crops (0 = whole batch)
   int alternate = 1;      // consecutive convolutions walk their tile lists in opposite directions (METRO_NO_ALTERNATE)
@@ -306,6 +319,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     r2_elems = std::max(r2_elems, size_t(u.out_side) * u.out_side * u.cb);
   }
   __half *raw[2] = {nullptr, nullptr}, *pre[2] = {nullptr, nullptr}, *r1 = nullptr, *r2 = nullptr;
+  if (const char *e = getenv("METRO_XFORM_MAX_CB")) h.xform_max_cb = atoi(e);
   if (!keep) {
     for (int i = 0; i < 2; ++i) {
       if ((st = alloc_half(&raw[i], raw_elems)) != METRO_OK) return st;
@@ -359,7 +373,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     // tensor instead of two.  Same arithmetic and rounding as the stored pre-activation, hence bit-identical.
     auto reads_raw = [&](size_t k) {
       static const bool no_xform = getenv("METRO_NO_XFORM") != nullptr;
-      return !no_xform && !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= 256;
+      return !no_xform && !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= h.xform_max_cb;
     };
     // conv1: 1x1, BN, ReLU on the pre-activation (resnet_v2.py:127-128)
     {
@@ -415,6 +429,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
   if (const char *e = getenv("METRO_HOST_CHUNK")) h.host_chunk = h.host_slice_u8 = atoi(e);
   if (const char *e = getenv("METRO_HOST_TAIL")) h.host_tail = atoi(e);
   if (const char *e = getenv("METRO_STEM_CHUNK")) h.stem_chunk = atoi(e);
+  if (const char *e = getenv("METRO_GRAPH_MAX_BATCH")) h.graph_max_batch = atoi(e);
   // ---- logits (resnet_v2.py:234-236) -> head tensor ----
   {
     const size_t eh = size_t(pl.feat_side) * pl.feat_side * pl.logits.cout;
@@ -443,6 +458,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
   }
   h.weight_bytes = A.uploaded;
   if (getenv("METRO_NO_DATAFLOW")) h.dataflow = 0;
+  if (getenv("METRO_DF_KEEP_ALTERNATE")) h.df_forward = 0;
   if (keep) h.dataflow = 0;      // debug handles keep grid-wide dependencies
   {
     void *q = nullptr;
@@ -520,6 +536,7 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
     prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;     // the root kernel walks forwards
     prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     set_dataflow(h, li, prm);
+    if (prm.dep_flags && h->df_forward) prm.reverse = 0;
     if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
@@ -542,6 +559,9 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
     prm.reverse = h->alternate ? (li & 1) ^ 1 : 0;
     prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     set_dataflow(h, int(li), prm);
+    // a layer that follows its producer crop by crop walks the tile list in the producer's order, so that the CTAs
+    // which replace the producer's early finishers start on crops that are already complete
+    if (prm.dep_flags && h->df_forward) prm.reverse = 0;
     if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
@@ -563,17 +583,9 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
   return METRO_OK;
 }
 
-metro_status run(metro_handle *h, const void *images, bool u8, int n, float *poses, cudaStream_t s, Timer *t) {
-  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
-  if (n < 0 || n > h->max_batch) return fail(METRO_ERR_VALUE, "batch %d outside [0, max_batch=%d]", n, h->max_batch);
-  if (n == 0) return METRO_OK;
-  if (!images || !poses) return fail(METRO_ERR_VALUE, "null image / pose buffer");
-  METRO_CUDA(cudaSetDevice(h->device));
-  if (t) {
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
-    t->ev.push_back(e); t->names.push_back("start");
-  }
-  if (h->strict) return strict_run(h->strict, images, u8, n, poses, s);
+// one call's launch sequence on stream `s` (capturable: nothing but stream operations, no handle state that a replay
+// would need changed)
+metro_status run_direct(metro_handle *h, const void *images, bool u8, int n, float *poses, cudaStream_t s, Timer *t) {
   {
     metro_status rst = reset_dataflow(h, s);
     if (rst != METRO_OK) return rst;
@@ -593,6 +605,58 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
   metro_status st = run_stem(h, images, u8, n, 0, 0, s, t);
   if (st != METRO_OK) return st;
   return run_tail(h, n, 0, 0, poses, s, t);
+}
+
+metro_status run(metro_handle *h, const void *images, bool u8, int n, float *poses, cudaStream_t s, Timer *t) {
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  if (n < 0 || n > h->max_batch) return fail(METRO_ERR_VALUE, "batch %d outside [0, max_batch=%d]", n, h->max_batch);
+  if (n == 0) return METRO_OK;
+  if (!images || !poses) return fail(METRO_ERR_VALUE, "null image / pose buffer");
+  METRO_CUDA(cudaSetDevice(h->device));
+  if (t) {
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+    t->ev.push_back(e); t->names.push_back("start");
+  }
+  if (h->strict) return strict_run(h->strict, images, u8, n, poses, s);
+  if (t || n > h->graph_max_batch) return run_direct(h, images, u8, n, poses, s, t);
+  // ---- small batch: replay a captured graph of the same call (same batch, dtype and buffers) ----
+  metro_handle::GraphEntry *e = nullptr;
+  for (auto &g : h->graphs)
+    if (g.n == n && g.u8 == u8 && g.images == images && g.poses == poses) e = &g;
+  if (!e) {
+    constexpr size_t kMaxGraphs = 8;
+    if (h->graphs.size() >= kMaxGraphs) {          // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+      if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+      if (h->graphs[lru].graph) cudaGraphDestroy(h->graphs[lru].graph);
+      h->graphs.erase(h->graphs.begin() + lru);
+    }
+    h->graphs.emplace_back();
+    e = &h->graphs.back();
+    e->n = n; e->u8 = u8; e->images = images; e->poses = poses;
+  }
+  e->last_use = ++h->graph_clock;
+  if (e->failed || e->seen++ == 0) return run_direct(h, images, u8, n, poses, s, nullptr);   // first sight: run as is
+  if (!e->exec) {
+    if (!h->cap_stream) METRO_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    bool ok = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const metro_status cst = run_direct(h, images, u8, n, poses, h->cap_stream, nullptr);
+      ok = cudaStreamEndCapture(h->cap_stream, &e->graph) == cudaSuccess && cst == METRO_OK && e->graph;
+    }
+    if (ok) ok = cudaGraphInstantiate(&e->exec, e->graph, 0) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+      e->exec = nullptr; e->failed = true;
+      return run_direct(h, images, u8, n, poses, s, nullptr);
+    }
+  }
+  METRO_CUDA(cudaGraphLaunch(e->exec, s));
+  ++h->graph_replays;
+  return METRO_OK;
 }
 
 }  // namespace
@@ -679,6 +743,11 @@ metro_status metro_destroy(metro_handle *h) {
   if (h->stage_img) cudaFree(h->stage_img);
   if (h->stage_pose) cudaFree(h->stage_pose);
   if (h->strict) strict_destroy(h->strict);
+  for (auto &g : h->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
   return METRO_OK;
 }
@@ -945,6 +1014,15 @@ metro_status metro_debug_read(metro_handle *h, const char *name, void *host_buf,
     METRO_CUDA(cudaDeviceSynchronize());
     METRO_CUDA(cudaMemcpy(host_buf, it->second.first, n_el * esize, cudaMemcpyDeviceToHost));
   }
+  return METRO_OK;
+}
+
+metro_status metro_graph_stats(const metro_handle *h, int32_t *graphs, int64_t *replays) {
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  int32_t k = 0;
+  for (const auto &g : h->graphs) k += g.exec != nullptr;
+  if (graphs) *graphs = k;
+  if (replays) *replays = int64_t(h->graph_replays);
   return METRO_OK;
 }
 

@@ -183,6 +183,15 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
     const int bytes = (px1 - px0) * C * esize;
     for (int off = tid * 128; off < bytes; off += int(blockDim.x) * 128)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
+    // The first `early` CTAs of a launch fit next to the previous launch's CTAs (the grid leaves that many residency
+    // slots free), so they start while it is still streaming: they pull the WHOLE input of this launch into L2, in
+    // equal shares, underneath the previous launch -- the later CTAs then find their item in L2.
+    if (int(blockIdx.x) < p.early) {
+      const size_t total = size_t(p.n) * P * C * esize;
+      const unsigned char *base = static_cast<const unsigned char *>(p.head);
+      for (size_t off = (size_t(blockIdx.x) * blockDim.x + tid) * 128; off < total; off += size_t(p.early) * blockDim.x * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
   }
   if (p.dep_flags) {
     // one thread polls the crop's counter (acquire, GPU scope); the barrier extends the ordering to the CTA
@@ -483,6 +492,21 @@ metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
   });
   if (cst != METRO_OK) return cst;
   const dim3 grid(unsigned(L.n) * unsigned(L.splits)), block(unsigned((L.slots * L.lanes + 31) & ~31));
+  SoftargmaxLaunch LL = L;
+  {
+    // L2 prefetch ahead of the dependency wait: only where it can pay -- one CTA per crop (a split crop's cluster
+    // cannot start early) and an input that fits L2 several times over (measured: 318 MB inputs thrash, -20 %)
+    static PerDeviceOnce sm_once;
+    static int sms[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    sm_once.run([&] { METRO_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev)); return METRO_OK; });
+    const size_t total = size_t(L.n) * L.H * L.W * L.C * (L.head_f16 ? 2 : 4);
+    if (L.splits != 1 || total > size_t(48) << 20) LL.l2_prefetch = 0;
+    const int slots = MINB * sms[dev];
+    static const bool no_early = std::getenv("METRO_SAM_NO_EARLY") != nullptr;
+    LL.early = (LL.l2_prefetch && !no_early && int(grid.x) < slots && int(grid.x) > slots / 2) ? slots - int(grid.x) : 0;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = sm; cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -503,11 +527,11 @@ metro_status launch_t(const SoftargmaxLaunch &L, cudaStream_t stream) {
   cfg.attrs = attr; cfg.numAttrs = unsigned(n_attr);
   static const bool want_prof = std::getenv("METRO_SAM_PROF") != nullptr;
   if (!want_prof) {
-    METRO_CUDA(cudaLaunchKernelEx(&cfg, softargmax_kernel<VEC, F16, CH, MAXT, MINB>, L));
+    METRO_CUDA(cudaLaunchKernelEx(&cfg, softargmax_kernel<VEC, F16, CH, MAXT, MINB>, LL));
     return METRO_OK;
   }
   // debug: per-CTA phase durations in SM clocks (launch -> dependency wait -> stream -> records -> merge -> output)
-  SoftargmaxLaunch P = L;
+  SoftargmaxLaunch P = LL;
   const size_t n_ctas = size_t(grid.x);
   METRO_CUDA(cudaMalloc(&P.prof, n_ctas * 8 * sizeof(long long)));
   METRO_CUDA(cudaMemsetAsync(P.prof, 0, n_ctas * 8 * sizeof(long long), stream));

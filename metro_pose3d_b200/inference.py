@@ -194,6 +194,12 @@ class MetroModel:
         _lib.check(self.lib.metro_launch_count(self._h, n, C.byref(k)))
         return k.value
 
+    def graph_stats(self):
+        """(instantiated CUDA graphs, replays so far) of the small-batch executor (metro_graph_stats)."""
+        g, r = C.c_int32(0), C.c_int64(0)
+        _lib.check(self.lib.metro_graph_stats(self._h, C.byref(g), C.byref(r)))
+        return g.value, r.value
+
     def workspace_bytes(self, n: int = 0) -> int:
         """Device bytes the handle holds for batches of up to ``n`` crops (0 = its whole arena)."""
         b = C.c_uint64(0)

@@ -23,7 +23,7 @@ EXPORTS = [
     'metro_last_error', 'metro_version', 'metro_blob_floats', 'metro_plan_describe', 'metro_create',
     'metro_destroy', 'metro_workspace_bytes', 'metro_get_joint_info', 'metro_infer', 'metro_infer_host', 'metro_infer_u8', 'metro_infer_host_u8', 'metro_to_orig_cam',
     'metro_softargmax_workspace_bytes', 'metro_softargmax', 'metro_conv2d', 'metro_debug_read',
-    'metro_profile', 'metro_launch_count',
+    'metro_profile', 'metro_launch_count', 'metro_graph_stats',
 ]
 
 
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     lib.metro_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     lib.metro_profile.argtypes = [vp, vp, i32, vp, vp, C.c_char_p, C.c_size_t, C.POINTER(i32)]
     lib.metro_launch_count.argtypes = [vp, i32, C.POINTER(i32)]
+    lib.metro_graph_stats.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_int64)]
     for name in EXPORTS:
         if name not in ('metro_last_error', 'metro_version'):
             getattr(lib, name).restype = C.c_int

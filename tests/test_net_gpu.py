@@ -200,3 +200,31 @@ def test_uint8_host_path_equals_device_path():
     assert np.array_equal(host, dev)
     with pytest.raises(ValueError):
         model.infer_host(u8.numpy().astype(np.int32))
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """Small batches are replayed from a captured CUDA graph (metro_graph_stats) the second time the same buffers are
+    seen; the results must equal the direct launches bit for bit, for new image CONTENTS in the same buffer too."""
+    import torch
+    from metro_pose3d_b200.inference import MetroModel
+    w = synth_weights(NetSpec('resnet_v2_50', 32, 17), 0)
+    model = MetroModel('resnet_v2_50', 32, 'h36m', weights=w, max_batch=4)
+    imgs = [torch.from_numpy(synth_images(4, seed=50 + i)).cuda() for i in range(3)]
+    direct = []
+    for x in imgs:                                       # fresh buffers every call: never replayed
+        direct.append(model.infer(x.clone(), out=torch.empty((4, 17, 3), device='cuda')).cpu().numpy())
+    assert model.graph_stats() == (0, 0)
+    buf = torch.empty_like(imgs[0])
+    out = torch.empty((4, 17, 3), device='cuda')
+    for rep in range(2):
+        for i, x in enumerate(imgs):
+            buf.copy_(x)
+            got = model.infer(buf, out=out).cpu().numpy()
+            assert np.array_equal(got, direct[i]), (rep, i)
+    graphs, replays = model.graph_stats()
+    assert graphs == 1 and replays == 5                  # first sight runs directly, the next five are replays
+    # uint8 feed of the same batch size: its own graph
+    u8 = torch.randint(0, 256, (4, 256, 256, 3), dtype=torch.uint8, device='cuda')
+    a = model.infer(u8, out=out).cpu().numpy()
+    b = model.infer(u8, out=out).cpu().numpy()
+    assert np.array_equal(a, b) and model.graph_stats()[0] == 2
