@@ -61,6 +61,11 @@ struct alignas(64) ConvGemmParams {
   const unsigned int *dep_done;
   unsigned int dep_ctas;
   unsigned int *sig_done;
+  // conv_chain.cu (conv3 of a unit + conv1 of the next in one kernel): the second convolution's weights [cout1][cout]
+  // K-major, its folded BN, and the shared-memory offset of the pre-activation operand buffer; o2map = its output
+  CUtensorMap w1map;
+  const float *scale1c, *shift1c;
+  int cout1, off_a2;
 };
 
 struct ConvGemmLaunch {
@@ -71,6 +76,7 @@ struct ConvGemmLaunch {
   double flops_per_img = 0;
   unsigned int sig_expected = 0;   // what this layer's counters reach per crop: (ho * wo / 32) x n_tiles
   bool signals = false;            // long tiles (a whole crop or more per CTA tile): worth a report per tile
+  bool chain = false;              // conv_chain.cu kernel (prm.cout1 > 0)
 };
 
 // Tensor-map helpers (driver entry point resolved at run time; no link-time libcuda dependency).
@@ -91,6 +97,11 @@ metro_status conv_gemm_geometry(ConvGemmParams &p, int out_side);
 metro_status conv_gemm_launch(const ConvGemmLaunch &L, const ConvGemmParams &prm, int num_sms, cudaStream_t stream);
 // CTAs the launch of `prm` runs (what its sig_done word reaches)
 int conv_gemm_grid(const ConvGemmParams &prm, int num_sms);
+
+// ---- conv_chain.cu: conv3 (+ shortcut) of unit u and conv1 of unit u + 1 in one kernel ----
+metro_status conv_chain_plan_smem(ConvGemmParams &p);
+metro_status conv_chain_launch(const ConvGemmParams &prm, int num_sms, cudaStream_t stream);
+int conv_chain_grid(const ConvGemmParams &prm, int num_sms);
 // Packs HWIO float32 filters into [cout_pad][K] fp16 in the kernel's K-block order; `w2` (1x1,
 // [cin2][cout]) is appended along K.
 void conv_gemm_pack_weights(const float *w_hwio, int k, int cin, int cout, const float *w2, int cin2,

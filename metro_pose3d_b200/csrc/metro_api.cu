@@ -91,6 +91,10 @@ struct GemmSpec {
   const __half *res = nullptr; int res_stride = 0, res_shift = 0, res_side = 0;
   void *out1 = nullptr; bool out1_f32 = false;
   __half *out2 = nullptr;
+  // chained second convolution (conv_chain.cu): 1x1 on y2 = relu(fp16(y) * scale2 + shift2), BN + ReLU, -> out_c
+  const float *w_c = nullptr; int cout_c = 0;
+  std::vector<float> scale_c, shift_c;
+  __half *out_c = nullptr;
 };
 
 metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L) {
@@ -104,6 +108,12 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   std::memset(&p, 0, sizeof p);
   L.direct = g.out1_f32 || (g.cout % 64 != 0);   // the logits head (136 / 152 channels, fp32 or fp16)
   L.block_n = conv_gemm_pick_block_n(g.cout, L.direct, (long long)g.n_max * g.out_side * g.out_side);
+  L.chain = g.cout_c > 0;
+  if (L.chain) {
+    if (L.direct || g.k != 1 || g.stride != 1 || g.out2 || g.cout % 256 != 0 || (g.cout_c != 64 && g.cout_c != 128 && g.cout_c != 256))
+      return fail(METRO_ERR_VALUE, "%s: this geometry cannot be chained", g.name.c_str());
+    L.block_n = 128;                               // conv3 tiles of 128 channels (conv_chain.cu)
+  }
   if (L.direct && (g.out2 || g.res)) return fail(METRO_ERR_VALUE, "%s: this output shape excludes a residual / second output", g.name.c_str());
   if (g.res && g.cin2) return fail(METRO_ERR_VALUE, "%s: identity and projection shortcuts are exclusive", g.name.c_str());
   if (g.res) {
@@ -171,9 +181,20 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   float *d = nullptr;
   st = arena.upload(&d, g.scale, cout_pad); if (st != METRO_OK) return st; p.scale = d;
   st = arena.upload(&d, g.shift, cout_pad); if (st != METRO_OK) return st; p.shift = d;
-  if (g.out2) {
+  if (g.out2 || L.chain) {
     st = arena.upload(&d, g.scale2, cout_pad); if (st != METRO_OK) return st; p.scale2 = d;
     st = arena.upload(&d, g.shift2, cout_pad); if (st != METRO_OK) return st; p.shift2 = d;
+  }
+  if (L.chain) {
+    // second convolution: weights [cout_c][cout] K-major (K order = conv3's output channels), boxes of cout_c / 2 rows
+    std::vector<__half> packed_c(size_t(g.cout_c) * g.cout);
+    conv_gemm_pack_weights(g.w_c, 1, g.cout, g.cout_c, nullptr, 0, g.cout_c, packed_c.data());
+    __half *d_wc = nullptr;
+    if ((st = arena.upload(&d_wc, packed_c)) != METRO_OK) return st;
+    if ((st = make_weight_tensor_map(&p.w1map, d_wc, g.cout_c, g.cout, g.cout_c)) != METRO_OK) return st;
+    st = arena.upload(&d, g.scale_c); if (st != METRO_OK) return st; p.scale1c = d;
+    st = arena.upload(&d, g.shift_c); if (st != METRO_OK) return st; p.shift1c = d;
+    p.cout1 = g.cout_c;
   }
   if (!g.ascale.empty()) {
     if (g.k != 1 || g.stride != 1 || g.cin2 || g.res || g.out2 || L.direct || L.block_n > 256)
@@ -188,13 +209,17 @@ metro_status build_gemm(DeviceArena &arena, const GemmSpec &g, ConvGemmLaunch &L
   if (!L.direct) {
     if (g.out1 && (st = make_out_tensor_map(&p.o1map, g.out1, m_rows, g.cout)) != METRO_OK) return st;
     if (g.out2 && (st = make_out_tensor_map(&p.o2map, g.out2, m_rows, g.cout)) != METRO_OK) return st;
+    if (L.chain && (st = make_out_tensor_map(&p.o2map, g.out_c, m_rows, g.cout_c)) != METRO_OK) return st;
   }
-  {
+  if (L.chain) {
+    if ((st = conv_chain_plan_smem(p)) != METRO_OK) return st;
+  } else {
     const int kb_tile = p.taps * p.cblk0 + (p.diag2 ? L.block_n / 64 : p.cblk1);
     if ((st = conv_gemm_plan_smem(L, kb_tile)) != METRO_OK) return st;
   }
   L.flops_per_img = 2.0 * g.out_side * g.out_side * double(g.cout) * K;
-  L.sig_expected = unsigned(g.out_side * g.out_side / 32) * unsigned(p.n_tiles);   // one report per epilogue warp (32 rows) and N tile
+  if (L.chain) L.flops_per_img += 2.0 * g.out_side * g.out_side * double(g.cout_c) * g.cout;
+  L.sig_expected = unsigned(g.out_side * g.out_side / 32) * unsigned(L.chain ? 1 : p.n_tiles);   // one report per epilogue warp (32 rows) and N tile (chain: per pixel tile)
   // Reports cost a GPU-scope release per epilogue warp and tile: affordable where a CTA tile is a whole crop or more
   // (maps of 16x16 and below: tiles of 5-50 us), not for the ~2 us tiles of the 64x64 / 32x32 layers (measured: +9 %
   // on the step with every layer reporting)
@@ -349,7 +374,9 @@ metro_status build_handle(metro_handle &h, const float *blob) {
   // the rotating buffers are re-used, in other layouts, by the next slice's early layers.
   size_t stem_units = 0;
   while (stem_units < pl.units.size() && pl.units[stem_units].out_side >= 32) ++stem_units;
-  h.stem_gemms = int(3 * stem_units);
+  h.stem_gemms = 0;
+  static const bool no_chain = getenv("METRO_NO_CHAIN") != nullptr;
+  bool conv1_done = false;       // this unit's conv1 ran inside the previous unit's chained kernel (conv_chain.cu)
   for (size_t i = 0; i < pl.units.size(); ++i) {
     const UnitPlan &u = pl.units[i];
     const bool last = (i + 1 == pl.units.size());
@@ -376,7 +403,7 @@ metro_status build_handle(metro_handle &h, const float *blob) {
       return !no_xform && !keep && k > 0 && k < pl.units.size() && !pl.units[k].proj && pl.units[k].cb <= h.xform_max_cb;
     };
     // conv1: 1x1, BN, ReLU on the pre-activation (resnet_v2.py:127-128)
-    {
+    if (!conv1_done) {
       GemmSpec g; g.name = u.conv1.name; g.n_max = N; g.src = cur_pre; g.in_side = u.in_side; g.cin = u.cin;
       if (reads_raw(i)) {
         g.src = cur_raw;
@@ -417,12 +444,29 @@ metro_status build_handle(metro_handle &h, const float *blob) {
       g.out1 = need_raw ? nraw : nullptr;
       g.out2 = reads_raw(i + 1) ? nullptr : npre;
       const int64_t next_bn = last ? pl.postnorm_off : pl.units[i + 1].preact_off;
-      if (g.out2) bn_affine(blob + next_bn, u.depth, g.scale2, g.shift2);
+      // Chain this conv3 with the NEXT unit's conv1 (conv_chain.cu) when that unit has an identity shortcut (it needs
+      // the raw sum in HBM, never the pre-activation) and a bottleneck of <= 256 channels (the second accumulator has
+      // to fit tensor memory next to the double-buffered first): the pre-activation stays on chip and the widest
+      // tensor of the unit is not read back.  Not across the stem boundary of the sliced host path.
+      const bool chain = !no_chain && !keep && !last && !pl.units[i + 1].proj && pl.units[i + 1].cb <= 256 &&
+                         u.depth % 256 == 0 && u.depth <= 1024 && i + 1 != stem_units;
+      if (chain) {
+        const UnitPlan &v = pl.units[i + 1];
+        g.name = u.conv3.name + "+" + v.conv1.name;
+        g.out2 = nullptr;
+        bn_affine(blob + next_bn, u.depth, g.scale2, g.shift2);
+        g.w_c = blob + v.conv1.w_off; g.cout_c = v.cb; g.out_c = r1;
+        bn_affine(blob + v.conv1.bn_off, v.cb, g.scale_c, g.shift_c);
+      } else if (g.out2) {
+        bn_affine(blob + next_bn, u.depth, g.scale2, g.shift2);
+      }
       if ((st = build_gemm(A, g, L)) != METRO_OK) return st;
       h.gemms.push_back(L);
       h.debug[u.name + "/out"] = {need_raw ? nraw : nullptr, eo};
       h.debug[u.name + "/pre"] = {g.out2 ? npre : nullptr, eo};
+      conv1_done = chain;
     }
+    if (i + 1 == stem_units) h.stem_gemms = int(h.gemms.size());
     cur_raw = nraw; cur_pre = npre;
   }
   if (getenv("METRO_NO_ALTERNATE")) h.alternate = 0;
@@ -496,7 +540,7 @@ void set_dataflow(metro_handle *h, int li, ConvGemmParams &prm) {
   if (h->gemms[li].signals) {
     prm.sig_flags = h->flags + size_t(li + 1) * N;
     prm.sig_done = done + li + 1;
-    h->df_launched[li + 1] += unsigned(conv_gemm_grid(prm, h->num_sms));
+    h->df_launched[li + 1] += unsigned(h->gemms[li].chain ? conv_chain_grid(prm, h->num_sms) : conv_gemm_grid(prm, h->num_sms));
   }
 }
 
@@ -537,7 +581,7 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
     prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     set_dataflow(h, li, prm);
     if (prm.dep_flags && h->df_forward) prm.reverse = 0;
-    if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
+    if ((st = L.chain ? conv_chain_launch(prm, h->num_sms, s) : conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
   return METRO_OK;
@@ -562,7 +606,7 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
     // a layer that follows its producer crop by crop walks the tile list in the producer's order, so that the CTAs
     // which replace the producer's early finishers start on crops that are already complete
     if (prm.dep_flags && h->df_forward) prm.reverse = 0;
-    if ((st = conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
+    if ((st = L.chain ? conv_chain_launch(prm, h->num_sms, s) : conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
   SoftargmaxLaunch sl = h->sam;

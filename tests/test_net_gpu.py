@@ -210,9 +210,10 @@ def test_cuda_graph_replay_is_bit_identical():
     w = synth_weights(NetSpec('resnet_v2_50', 32, 17), 0)
     model = MetroModel('resnet_v2_50', 32, 'h36m', weights=w, max_batch=4)
     imgs = [torch.from_numpy(synth_images(4, seed=50 + i)).cuda() for i in range(3)]
-    direct = []
-    for x in imgs:                                       # fresh buffers every call: never replayed
-        direct.append(model.infer(x.clone(), out=torch.empty((4, 17, 3), device='cuda')).cpu().numpy())
+    direct, keep = [], []
+    for x in imgs:                                       # distinct buffers every call (kept alive): never replayed
+        keep.append((x.clone(), torch.empty((4, 17, 3), device='cuda')))
+        direct.append(model.infer(keep[-1][0], out=keep[-1][1]).cpu().numpy())
     assert model.graph_stats() == (0, 0)
     buf = torch.empty_like(imgs[0])
     out = torch.empty((4, 17, 3), device='cuda')
@@ -228,3 +229,4 @@ def test_cuda_graph_replay_is_bit_identical():
     a = model.infer(u8, out=out).cpu().numpy()
     b = model.infer(u8, out=out).cpu().numpy()
     assert np.array_equal(a, b) and model.graph_stats()[0] == 2
+    del keep
