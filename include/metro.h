@@ -161,6 +161,28 @@ metro_status metro_softargmax_workspace_bytes(const metro_softargmax_desc *d, in
 metro_status metro_softargmax(const metro_softargmax_desc *d, const void *head_dev, int32_t n,
                               float *poses_dev, void *workspace_dev, void *stream);
 
+/* The same decode with the evaluation graph's other fetches.  coords01_dev [n, n_joints_model, 3]
+ * receives the heatmap coordinates in [0,1] of every model joint (what net_output_to_heatmap_and_coords
+ * returns, volumetric.py:234) -- the input of the absolute-scale variants below; poses_dev may then be NULL. */
+metro_status metro_softargmax_coords(const metro_softargmax_desc *d, const void *head_dev, int32_t n,
+                                     float *poses_dev, float *coords01_dev, void *workspace_dev, void *stream);
+/* Whole network with that second fetch (tensor-core or strict handles; float32 images). */
+metro_status metro_infer_coords(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev,
+                                float *coords01_dev, void *stream);
+/* t.heatmap_pred_z = reduce_sum(softmaxed, axis=[2, 3]) (volumetric.py:165): the depth marginal of every model
+ * joint's heatmap, out_dev float32 [n, n_joints_model, depth].  head_dev as for metro_softargmax. */
+metro_status metro_heatmap_z(const metro_softargmax_desc *d, const void *head_dev, int32_t n, float *out_dev,
+                             void *stream);
+/* Absolute-scale variant 'true-root-depth' of build_inference_model (volumetric.py:190-198) and back_project
+ * (:285): out[b,c,:] = (inv_intrinsics[b] @ [u, v, 1]) * ((z[b,c] - z[b,root]) * box_size_mm + z_offset[b]) with
+ * (u, v) = heatmap_to_image(coords01[b,c,:2]) (:288-295) and root = the LAST joint.  coords01_dev / out_dev float32
+ * [n, n_joints, 3] (model joint order), inv_intrinsics_dev float32 [n,3,3] row-major, z_offset_dev float32 [n]: the
+ * true root depth ('true-root-depth') or the offset a bone-length fit produced ('bone-lengths*', whose optimiser is
+ * host code in the reference too: a scipy py_func, src/model/bone_length_based_backproj.py). */
+metro_status metro_back_project(const float *coords01_dev, const float *inv_intrinsics_dev, const float *z_offset_dev,
+                                int32_t n, int32_t n_joints, int32_t stride, int32_t centered_stride, int32_t proc_side,
+                                float box_size_mm, float *out_dev, void *stream);
+
 /* ---- post-path: back into the original camera frame.  Replaces to_orig_cam
  *      (volumetric.py:277-282): out[b,c,:] = R[b] @ poses[b,c',:], c' = c where det(R[b]) > 0, else
  *      mirror_mapping[c] (the crop was flipped, data_loading.py:80-83; JointInfo.mirror_mapping,

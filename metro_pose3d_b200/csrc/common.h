@@ -57,6 +57,9 @@ struct SoftargmaxLaunch {
   int tpj;                 // threads per joint in the merge (power of two <= 32)
   long long *prof;         // debug (METRO_SAM_PROF): 8 clock64 stamps per CTA, or null
   int head_f16;
+  float *coords01;         // optional second output [n][J][3]: heatmap coordinates in [0,1] of every MODEL joint
+                           // (what net_output_to_heatmap_and_coords returns, volumetric.py:234); `out` may then be null
+  double unmul_x, unmul_y, unmul_z;   // 1 / mm-per-unit: back from the scaled expectations to [0,1]
   int l2_prefetch;         // pull the item's bytes into L2 ahead of the dependency wait (stand-alone launches)
   int early;               // CTAs [0, early) also prefetch an equal share of the whole input (they start early)
   // dataflow (ptx.cuh): wait for the crop's counter of the logits layer instead of for the whole previous grid
@@ -70,5 +73,8 @@ metro_status softargmax_launch(const SoftargmaxLaunch &L, cudaStream_t stream);
 // ---- post-path transforms ---------------------------------------------------------------------------
 metro_status to_orig_cam_launch(const float *poses, const float *rot, const int32_t *mirror, int n, int j, float *out,
                                 cudaStream_t stream);
+metro_status back_project_launch(const float *coords01, const float *inv_k, const float *z_off, int n, int j, double lrc,
+                                 double add_xy, double box, float *out, cudaStream_t stream);
+metro_status heatmap_z_launch(const void *head, bool f16, int n, int side, int j, int depth, float *out, cudaStream_t stream);
 
 }  // namespace metro

@@ -37,7 +37,10 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32;
 constexpr int kSmemLimit = 232448;
 constexpr int kABytes = kTileM * kTileK * 2;  // 16 KB: 128 pixel rows of one 64-channel K block
-constexpr int kStageBytes = 2 * kABytes;      // + up to 128 weight rows
+constexpr int kStageBytes = kABytes + 8192;   // + 64 weight rows; a conv1 K block (weights only, <= 16 KB) starts at offset 0.
+                                              // Slots are as small as the blocks allow: the kernel is bound by the bytes it
+                                              // keeps in flight (role timers: both producers wait for slots while the MMA
+                                              // thread waits for data), so the ring should be all payload
 constexpr int kA2Bytes = 2 * kABytes;         // one 128-channel tile of the pre-activation = two K blocks of conv1
 
 // barrier slots (uint64): full[8] empty[8] tfull3[2] tempty3[2] a2full[2] a2empty[2] tfull1 tempty1
@@ -112,6 +115,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
   if (!p.dep_flags) ptx::griddep_wait();
   ptx::griddep_launch_dependents();
   const int n_end = p.m_total / (p.ho * p.wo);
+  // role timers (METRO_ROLE_PROF, same slots as conv_gemm.cu; 12 = epilogue waits for the operand buffer, 13 = MMA
+  // waits for the pre-activation, 14 = MMA waits for the conv1 accumulator, 15 = weight producer waits for a slot)
+  const bool prof = p.prof != nullptr;
+  const long long t_start = prof ? clock64() : 0;
+  long long *pr = p.prof + size_t(blockIdx.x) * 16;
 
   if (warp == 0 || warp == 3) {
     // ================================ TMA producers ===============================
@@ -120,10 +128,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       int stage = 0;
       uint32_t phase = 0;
       bool dep_all_done = false;
+      long long t_wait = 0;
       const uint32_t full0 = ptx::mapa(ptx::smem_u32(full), 0);     // operands of both CTAs land on the leader's barrier
       // waits for the slot; the leader's activation producer arms the byte count of BOTH CTAs' boxes
       auto acquire = [&](uint32_t bytes_per_cta) -> unsigned char * {
+        const long long t0 = prof ? clock64() : 0;
         ptx::mbar_wait(empty + stage, phase ^ 1);
+        if (prof) t_wait += clock64() - t0;
         if (is_a && rank == 0) ptx::mbar_arrive_expect_tx(full + stage, 2 * bytes_per_cta);
         return tiles + stage * kStageBytes;
       };
@@ -131,7 +142,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       auto conv1_blocks = [&](int nt, int) {          // weights of conv1 for K range [128 nt, 128 nt + 128)
         for (int kb2 = 0; kb2 < 2; ++kb2) {
           unsigned char *sa = acquire((BN1 / 2) * kTileK * 2);
-          if (!is_a) ptx::tma_load_2d_pair(sa + kABytes, &p.w1map, full0 + uint32_t(stage) * 8u, (nt * 2 + kb2) * kTileK, int(rank) * (BN1 / 2));
+          if (!is_a) ptx::tma_load_2d_pair(sa, &p.w1map, full0 + uint32_t(stage) * 8u, (nt * 2 + kb2) * kTileK, int(rank) * (BN1 / 2));
           advance();
         }
       };
@@ -180,6 +191,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         }
         conv1_blocks(NT3 - 1, 0);
       }
+      if (prof) pr[is_a ? 1 : 15] = t_wait;
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
@@ -190,18 +202,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       const uint32_t tm1 = tmem_base + 2 * kBN3;
       int stage = 0;
       uint32_t phase = 0, q = 0, it = 0;             // q: conv3 tiles issued so far (all items)
+      long long t_full = 0, t_acc = 0, t_a2 = 0, t_acc1 = 0;
+      auto timed_wait = [&](uint64_t *bar, uint32_t parity, long long &acc) {
+        const long long t0 = prof ? clock64() : 0;
+        ptx::mbar_wait(bar, parity);
+        if (prof) acc += clock64() - t0;
+      };
       auto next_stage = [&]() { if (++stage == stages) { stage = 0; phase ^= 1; } };
       // conv1 partial product over the pre-activation of conv3 tile j (global index qj)
       auto conv1_part = [&](int j, uint32_t qj) {
         const int b = j & 1;
-        ptx::mbar_wait(a2full + b, (qj >> 1) & 1);
-        if (j == 0) ptx::mbar_wait(tempty1, (it & 1) ^ 1);          // the previous pixel tile's conv1 accumulator is drained
+        timed_wait(a2full + b, (qj >> 1) & 1, t_a2);
+        if (j == 0) timed_wait(tempty1, (it & 1) ^ 1, t_acc1);      // the previous pixel tile's conv1 accumulator is drained
         ptx::tc_fence_after();
         for (int kb2 = 0; kb2 < 2; ++kb2) {
-          ptx::mbar_wait(full + stage, phase);
+          timed_wait(full + stage, phase, t_full);
           ptx::tc_fence_after();
           const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(a2buf + b * kA2Bytes + kb2 * kABytes));
-          const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(tiles + stage * kStageBytes + kABytes));
+          const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(tiles + stage * kStageBytes));
 #pragma unroll
           for (int k = 0; k < kTileK / 16; ++k) ptx::umma_f16_pair(tm1, da + 2 * k, db + 2 * k, idesc1, (j | kb2 | k) != 0);
           ptx::umma_commit_pair(empty + stage, 3);
@@ -212,11 +230,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       for (int item = pair; item < n_items; item += n_pairs, ++it) {
         for (int nt = 0; nt < NT3; ++nt, ++q) {
           const int b = nt & 1;
-          ptx::mbar_wait(tempty3 + b, ((q >> 1) & 1) ^ 1);
+          timed_wait(tempty3 + b, ((q >> 1) & 1) ^ 1, t_acc);
           ptx::tc_fence_after();
           const uint32_t d3 = tmem_base + b * kBN3;
           for (int kb = 0; kb < n1; ++kb) {
-            ptx::mbar_wait(full + stage, phase);
+            timed_wait(full + stage, phase, t_full);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(tiles + stage * kStageBytes);
             const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
@@ -237,6 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         conv1_part(NT3 - 1, q - 1);
         ptx::umma_commit_pair(tfull1, 3);
       }
+      if (prof) { pr[2] = t_full; pr[3] = t_acc; pr[13] = t_a2; pr[14] = t_acc1; pr[7] = it; }
     }
   } else if (warp >= kCtrlWarps) {
     // ================================ epilogue ====================================
@@ -259,12 +278,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
     const uint32_t a2full_0 = ptx::mapa(ptx::smem_u32(a2full + g), 0);
     const uint32_t tempty1_0 = ptx::mapa(ptx::smem_u32(tempty1), 0);
     uint32_t it = 0;
+    long long t_wacc = 0, t_busy = 0, t_wa2 = 0, t_wst = 0;
     for (int item = pair; item < n_items; item += n_pairs, ++it) {
       const int mp = p.reverse ? n_items - 1 - item : item;
       const int m0 = p.m_base + (2 * mp + int(rank)) * kTileM + qw * 32;
       for (int nt = g; nt < NT3; nt += 2) {
         const uint32_t qg = it * uint32_t(NT3) + uint32_t(nt);
+        const long long w0 = prof ? clock64() : 0;
         ptx::mbar_wait(tfull3 + g, (qg >> 1) & 1);
+        const long long w1 = prof ? clock64() : 0;
+        t_wacc += w1 - w0;
         ptx::tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < kBN3 / 32; ++c) {
@@ -302,8 +325,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
             }
           }
           if (p.has_out1) {
+            const long long s0 = prof ? clock64() : 0;
             if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store from this staging box has been read
             __syncwarp();
+            if (prof) t_wst += clock64() - s0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) sts_v4(st + row_a + ((uint32_t(j) ^ sw) << 4), o1[j]);
             ptx::fence_proxy_async();
@@ -314,7 +339,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
             }
           }
           // the pre-activation goes to the operand buffer of conv1: K block c / 2, 16-byte chunks 4 (c % 2) + j of the row
-          if (c == 0) ptx::mbar_wait(a2empty + g, ((qg >> 1) & 1) ^ 1);
+          if (c == 0) {
+            const long long s0 = prof ? clock64() : 0;
+            ptx::mbar_wait(a2empty + g, ((qg >> 1) & 1) ^ 1);
+            if (prof) t_wa2 += clock64() - s0;
+          }
           const uint32_t a2 = a2row + uint32_t(c >> 1) * uint32_t(kABytes);
 #pragma unroll
           for (int j = 0; j < 4; ++j) sts_v4(a2 + ((uint32_t((c & 1) * 4 + j) ^ uint32_t(row & 7)) << 4), o2[j]);
@@ -322,9 +351,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         ptx::fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(a2full_0);
+        if (prof) t_busy += clock64() - w1;
       }
       // ---- conv1 of the next unit: BN + ReLU, this group's half of the columns ----
+      const long long w2 = prof ? clock64() : 0;
       ptx::mbar_wait(tfull1, it & 1);
+      const long long w3 = prof ? clock64() : 0;
+      t_wacc += w3 - w2;
       ptx::tc_fence_after();
       constexpr int kChunks1 = BN1 / 2 / 32;
 #pragma unroll 1
@@ -371,8 +404,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         ptx::fence_proxy_async_all();
         if (m0 < p.m_total) ptx::flag_signal(p.sig_flags + m0 / (p.ho * p.wo));
       }
+      if (prof) t_busy += clock64() - w3;
     }
     if (lane == 0) ptx::bulk_wait<0>();              // shared memory must outlive the last TMA store
+    if (prof && e == 0 && lane == 0) { pr[4] = t_wacc; pr[5] = t_busy; pr[6] = t_wst; pr[12] = t_wa2; }
   }
 
   ptx::tc_fence_before();
@@ -386,6 +421,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
     ptx::fence_proxy_async_all();
     ptx::flag_signal(p.sig_done);
   }
+  if (prof && threadIdx.x == 0) pr[0] = clock64() - t_start;
 }
 
 template <int BN1>

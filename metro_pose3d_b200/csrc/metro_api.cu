@@ -257,6 +257,7 @@ struct metro_handle {
   std::string joint_names;       // the graph's constant fetches (main.py:128,140-141), '\n'-separated
   std::vector<int32_t> joint_edges;
   size_t weight_bytes = 0;       // part of arena.total that does not scale with max_batch
+  float *coords01_out = nullptr; // metro_infer_coords: second fetch of the call in flight
   unsigned int *flags = nullptr; // dataflow counters [1 + gemms][max_batch]: row 0 = fused root, row 1 + i = gemms[i]
   // CUDA-graph executor for small batches (launch-bound: 52 launches of a few microseconds each): the launch
   // sequence of a call is captured once per (batch, dtype, buffers) and replayed
@@ -617,7 +618,8 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
   const size_t head_bytes = size_t(sl.H) * sl.W * sl.C * (sl.head_f16 ? 2 : 4);
   sl.n = n;
   sl.head = static_cast<const unsigned char *>(h->buf_head) + size_t(n_base) * head_bytes;
-  sl.out = poses + size_t(n_base) * sl.n_out * 3;
+  sl.out = poses ? poses + size_t(n_base) * sl.n_out * 3 : nullptr;
+  sl.coords01 = h->coords01_out ? h->coords01_out + size_t(n_base) * sl.J * 3 : nullptr;
   sl.counters = static_cast<unsigned int *>(h->sam_ws) + n_base;
   sl.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(h->sam_ws) +
                                            ((size_t(h->max_batch) * 4 + 255) & ~size_t(255))) +
@@ -970,13 +972,57 @@ metro_status metro_softargmax_workspace_bytes(const metro_softargmax_desc *d, in
 
 metro_status metro_softargmax(const metro_softargmax_desc *d, const void *head_dev, int32_t n, float *poses_dev,
                               void *workspace_dev, void *stream) {
+  if (n > 0 && !poses_dev) return fail(METRO_ERR_VALUE, "null device buffer");
+  return metro_softargmax_coords(d, head_dev, n, poses_dev, nullptr, workspace_dev, stream);
+}
+
+metro_status metro_heatmap_z(const metro_softargmax_desc *d, const void *head_dev, int32_t n, float *out_dev, void *stream) {
+  if (!d) return fail(METRO_ERR_VALUE, "null argument");
+  if (d->side <= 0 || d->n_joints_model <= 0 || d->depth <= 0 || n < 0) return fail(METRO_ERR_VALUE, "heatmap_z: bad shape");
+  if (d->head_dtype != METRO_F16 && d->head_dtype != METRO_F32) return fail(METRO_ERR_VALUE, "heatmap_z: bad head_dtype");
+  if (n == 0) return METRO_OK;
+  if (!head_dev || !out_dev) return fail(METRO_ERR_VALUE, "null device buffer");
+  return heatmap_z_launch(head_dev, d->head_dtype == METRO_F16, n, d->side, d->n_joints_model, d->depth, out_dev,
+                          static_cast<cudaStream_t>(stream));
+}
+
+metro_status metro_back_project(const float *coords01_dev, const float *inv_intrinsics_dev, const float *z_offset_dev, int32_t n,
+                                int32_t n_joints, int32_t stride, int32_t centered_stride, int32_t proc_side, float box_size_mm,
+                                float *out_dev, void *stream) {
+  if (n < 0 || n_joints <= 0 || stride <= 0 || proc_side <= 0) return fail(METRO_ERR_VALUE, "back_project: bad argument");
+  if (n == 0) return METRO_OK;
+  if (!coords01_dev || !inv_intrinsics_dev || !z_offset_dev || !out_dev) return fail(METRO_ERR_VALUE, "back_project: null device buffer");
+  const int last = proc_side - 1;                                  // volumetric.py:288-291
+  const double lrc = double(last - (last % stride) - 1);
+  return back_project_launch(coords01_dev, inv_intrinsics_dev, z_offset_dev, n, n_joints, lrc,
+                             centered_stride ? double(stride / 2) : 0.0, double(box_size_mm), out_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+metro_status metro_infer_coords(metro_handle *h, const float *images_dev, int32_t n, float *poses_dev, float *coords01_dev,
+                                void *stream) {
+  if (!h) return fail(METRO_ERR_VALUE, "handle is null");
+  if (n < 0 || n > h->max_batch) return fail(METRO_ERR_VALUE, "batch %d outside [0, max_batch=%d]", n, h->max_batch);
+  if (n == 0) return METRO_OK;
+  if (!images_dev || !coords01_dev) return fail(METRO_ERR_VALUE, "null image / coordinate buffer");
+  METRO_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->strict) return strict_run(h->strict, images_dev, false, n, poses_dev, s, coords01_dev);
+  h->coords01_out = coords01_dev;                                  // picked up by run_tail for this call only
+  const metro_status st = run_direct(h, images_dev, false, n, poses_dev, s, nullptr);
+  h->coords01_out = nullptr;
+  return st;
+}
+
+metro_status metro_softargmax_coords(const metro_softargmax_desc *d, const void *head_dev, int32_t n, float *poses_dev,
+                                     float *coords01_dev, void *workspace_dev, void *stream) {
   if (!d) return fail(METRO_ERR_VALUE, "null argument");
   SoftargmaxLaunch L;
   metro_status st = softargmax_plan(*d, n, L);
   if (st != METRO_OK) return st;
   if (n == 0) return METRO_OK;
-  if (!head_dev || !poses_dev || !workspace_dev) return fail(METRO_ERR_VALUE, "null device buffer");
-  L.head = head_dev; L.out = poses_dev;
+  if (!head_dev || (!poses_dev && !coords01_dev) || !workspace_dev) return fail(METRO_ERR_VALUE, "null device buffer");
+  L.head = head_dev; L.out = poses_dev; L.coords01 = coords01_dev;
   L.counters = static_cast<unsigned int *>(workspace_dev);
   L.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(workspace_dev) + ((size_t(n) * 4 + 255) & ~size_t(255)));
   return softargmax_launch(L, static_cast<cudaStream_t>(stream));

@@ -468,11 +468,19 @@ __global__ void __launch_bounds__(MAXT, MINB) softargmax_kernel(const Softargmax
     }
     __syncthreads();
   }
-  if (tid < p.n_out * 3)                  // n_out <= 64 and the CTA has >= 192 threads... or loops below
-    p.out[(size_t(img) * p.n_out) * 3 + tid] = float(s_c01[out_src] - s_c01[3 * p.root + out_ax]);
-  for (int i = tid + blockDim.x; i < p.n_out * 3; i += blockDim.x) {
-    const int jo = i / 3, a = i - 3 * jo;
-    p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
+  if (p.out) {
+    if (tid < p.n_out * 3)                // n_out <= 64 and the CTA has >= 192 threads... or loops below
+      p.out[(size_t(img) * p.n_out) * 3 + tid] = float(s_c01[out_src] - s_c01[3 * p.root + out_ax]);
+    for (int i = tid + blockDim.x; i < p.n_out * 3; i += blockDim.x) {
+      const int jo = i / 3, a = i - 3 * jo;
+      p.out[(size_t(img) * p.n_out) * 3 + i] = float(s_c01[3 * p.perm[jo] + a] - s_c01[3 * p.root + a]);
+    }
+  }
+  if (p.coords01) {                       // heatmap coordinates in [0,1], model joint order (volumetric.py:234)
+    for (int i = tid; i < J * 3; i += blockDim.x) {
+      const int a = i % 3;
+      p.coords01[size_t(img) * J * 3 + i] = float(s_c01[i] * (a == 0 ? p.unmul_x : (a == 1 ? p.unmul_y : p.unmul_z)));
+    }
   }
   if (prof) { stamp[5] = clock64(); stamp[7] = (long long)ptx::globaltimer(); }
 }
@@ -596,6 +604,9 @@ metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLa
   L.mul_x = L.W > 1 ? xy / double(L.W - 1) : 0.0;
   L.mul_y = L.H > 1 ? xy / double(L.H - 1) : 0.0;
   L.mul_z = L.D > 1 ? double(d.box_size_mm) / double(L.D - 1) : 0.0;
+  L.unmul_x = L.mul_x != 0.0 ? 1.0 / (L.mul_x * double(L.W - 1)) : 0.0;
+  L.unmul_y = L.mul_y != 0.0 ? 1.0 / (L.mul_y * double(L.H - 1)) : 0.0;
+  L.unmul_z = L.mul_z != 0.0 ? 1.0 / (L.mul_z * double(L.D - 1)) : 0.0;
   L.head_f16 = d.head_dtype == METRO_F16;
   L.slots = L.C / vec;
   L.vec = vec;

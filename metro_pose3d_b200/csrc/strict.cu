@@ -441,7 +441,13 @@ metro_status strict_build(const NetPlan &pl, const float *blob, int max_batch, i
   return METRO_OK;
 }
 
-metro_status strict_run(StrictNet *net, const void *images_dev, bool u8, int n, float *poses_dev, cudaStream_t s) {
+__global__ void strict_coords_kernel(const double *coords, float *out, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = float(coords[i]);
+}
+
+metro_status strict_run(StrictNet *net, const void *images_dev, bool u8, int n, float *poses_dev, cudaStream_t s,
+                        float *coords01_dev) {
   if (n == 0) return METRO_OK;
   const NetPlan &pl = net->plan;
   {
@@ -466,8 +472,13 @@ metro_status strict_run(StrictNet *net, const void *images_dev, bool u8, int n, 
   strict_decode_kernel<<<unsigned(n * pl.n_joints), 256, 0, s>>>(net->head, net->coords, pl.feat_side, pl.feat_side, pl.depth,
                                                                   pl.n_joints);
   const int tot = n * net->n_out * 3;
-  strict_metric_kernel<<<unsigned((tot + 127) / 128), 128, 0, s>>>(net->coords, poses_dev, n, pl.n_joints, net->n_out, net->d_perm,
-                                                                   net->lrc, net->add_xy, net->box, double(pl.proc_side));
+  if (poses_dev)
+    strict_metric_kernel<<<unsigned((tot + 127) / 128), 128, 0, s>>>(net->coords, poses_dev, n, pl.n_joints, net->n_out, net->d_perm,
+                                                                     net->lrc, net->add_xy, net->box, double(pl.proc_side));
+  if (coords01_dev) {
+    const int tc = n * pl.n_joints * 3;
+    strict_coords_kernel<<<unsigned((tc + 127) / 128), 128, 0, s>>>(net->coords, coords01_dev, tc);
+  }
   METRO_CUDA(cudaGetLastError());
   return METRO_OK;
 }

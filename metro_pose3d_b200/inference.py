@@ -133,6 +133,26 @@ class MetroModel:
             _lib.check(fn(self._h, images[lo:lo + cnt].data_ptr(), cnt, out[lo:lo + cnt].data_ptr(), stream))
         return out
 
+    def infer_coords(self, images, stream: Optional[int] = None):
+        """The evaluation graph's second fetch (metro_infer_coords): returns ``(poses [n,J_out,3] mm, coords01
+        [n,J_model,3])`` -- the heatmap coordinates in [0,1] that ``net_output_to_heatmap_and_coords`` returns
+        (volumetric.py:234), the input of ``back_project``."""
+        torch = _torch()
+        if images.dim() != 4 or tuple(images.shape[1:]) != (self.spec.proc_side, self.spec.proc_side, 3) or \
+                images.dtype != torch.float32 or not images.is_cuda or images.device.index != self.device:
+            raise ValueError(f'expected a float32 [N,{self.spec.proc_side},{self.spec.proc_side},3] tensor on cuda:{self.device}')
+        images = images.contiguous()
+        n = images.shape[0]
+        poses = torch.empty((n, self.n_joints_out, 3), dtype=torch.float32, device=images.device)
+        coords = torch.empty((n, self.n_joints_model, 3), dtype=torch.float32, device=images.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(images.device).cuda_stream
+        for lo in range(0, n, self.max_batch):
+            cnt = min(self.max_batch, n - lo)
+            _lib.check(self.lib.metro_infer_coords(self._h, images[lo:lo + cnt].data_ptr(), cnt, poses[lo:lo + cnt].data_ptr(),
+                                                   coords[lo:lo + cnt].data_ptr(), stream))
+        return poses, coords
+
     def infer_host(self, images: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Host buffers in / out (what ``sess.run`` does for numpy feeds, inference.py:26-27).  uint8 crops
         (the loader's format before improc.py:56-61) go through ``metro_infer_host_u8``: a quarter of the bytes."""
@@ -281,6 +301,50 @@ class SoftArgmax:
         _lib.check(self.lib.metro_softargmax(C.byref(self.desc), head.data_ptr(), n, out.data_ptr(),
                                              self._ws.data_ptr(), stream))
         return out
+
+
+    def coords(self, head):
+        """(poses, coords01): the decode with the heatmap coordinates in [0,1] of every model joint as a second output
+        (metro_softargmax_coords; volumetric.py:234)."""
+        torch = _torch()
+        out = self(head)                                  # validates, sizes the workspace
+        n = head.shape[0]
+        c01 = torch.empty((n, self.channels // self.desc.depth, 3), dtype=torch.float32, device=head.device)
+        stream = torch.cuda.current_stream(head.device).cuda_stream
+        _lib.check(self.lib.metro_softargmax_coords(C.byref(self.desc), head.contiguous().data_ptr(), n, out.data_ptr(),
+                                                    c01.data_ptr(), self._ws.data_ptr(), stream))
+        return out, c01
+
+    def heatmap_z(self, head):
+        """``t.heatmap_pred_z`` (volumetric.py:165): depth marginal of the softmaxed heatmap, [N, J_model, D]."""
+        torch = _torch()
+        n = head.shape[0]
+        out = torch.empty((n, self.channels // self.desc.depth, self.desc.depth), dtype=torch.float32, device=head.device)
+        stream = torch.cuda.current_stream(head.device).cuda_stream
+        _lib.check(self.lib.metro_heatmap_z(C.byref(self.desc), head.contiguous().data_ptr(), n, out.data_ptr(), stream))
+        return out
+
+
+def back_project(coords01, inv_intrinsics, z_offset, stride: int, centered_stride: bool = True, proc_side: int = 256,
+                 box_size_mm: float = 2200.0):
+    """The 'true-root-depth' branch of the reference's evaluation graph (src/model/volumetric.py:190-198,285) on device
+    tensors: coords01 float32 ``[N, J, 3]`` (root joint last), inv_intrinsics float32 ``[N, 3, 3]``, z_offset float32
+    ``[N]`` (the true root depth, or a bone-length fit's offset).  Returns absolute camera-frame ``[N, J, 3]`` mm."""
+    torch = _torch()
+    if coords01.dim() != 3 or coords01.shape[2] != 3 or coords01.dtype != torch.float32 or not coords01.is_cuda:
+        raise ValueError('expected a CUDA float32 [N, J, 3] tensor of heatmap coordinates')
+    n, j = coords01.shape[0], coords01.shape[1]
+    if tuple(inv_intrinsics.shape) != (n, 3, 3) or inv_intrinsics.dtype != torch.float32 or not inv_intrinsics.is_cuda:
+        raise ValueError(f'expected a CUDA float32 [{n}, 3, 3] tensor of inverse intrinsics')
+    if tuple(z_offset.shape) != (n,) or z_offset.dtype != torch.float32 or not z_offset.is_cuda:
+        raise ValueError(f'expected a CUDA float32 [{n}] tensor of depth offsets')
+    lib = _lib.load()
+    out = torch.empty_like(coords01)
+    stream = torch.cuda.current_stream(coords01.device).cuda_stream
+    _lib.check(lib.metro_back_project(coords01.contiguous().data_ptr(), inv_intrinsics.contiguous().data_ptr(),
+                                      z_offset.contiguous().data_ptr(), n, j, stride, int(centered_stride), proc_side,
+                                      box_size_mm, out.data_ptr(), stream))
+    return out
 
 
 def conv2d(x, w_hwio: np.ndarray, scale: np.ndarray, shift: np.ndarray, stride: int = 1, rate: int = 1,

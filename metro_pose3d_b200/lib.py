@@ -22,7 +22,8 @@ PRECISIONS = {'f16': METRO_PREC_F16, 'strict': METRO_PREC_STRICT, 'strict_f16': 
 EXPORTS = [
     'metro_last_error', 'metro_version', 'metro_blob_floats', 'metro_plan_describe', 'metro_create',
     'metro_destroy', 'metro_workspace_bytes', 'metro_get_joint_info', 'metro_infer', 'metro_infer_host', 'metro_infer_u8', 'metro_infer_host_u8', 'metro_to_orig_cam',
-    'metro_softargmax_workspace_bytes', 'metro_softargmax', 'metro_conv2d', 'metro_debug_read',
+    'metro_softargmax_workspace_bytes', 'metro_softargmax', 'metro_softargmax_coords', 'metro_infer_coords', 'metro_heatmap_z',
+    'metro_back_project', 'metro_conv2d', 'metro_debug_read',
     'metro_profile', 'metro_launch_count', 'metro_graph_stats',
 ]
 
@@ -98,6 +99,10 @@ def load() -> C.CDLL:
     lib.metro_to_orig_cam.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.metro_softargmax_workspace_bytes.argtypes = [C.POINTER(SoftargmaxDesc), i32, C.POINTER(u64)]
     lib.metro_softargmax.argtypes = [C.POINTER(SoftargmaxDesc), vp, i32, vp, vp, vp]
+    lib.metro_softargmax_coords.argtypes = [C.POINTER(SoftargmaxDesc), vp, i32, vp, vp, vp, vp]
+    lib.metro_infer_coords.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.metro_heatmap_z.argtypes = [C.POINTER(SoftargmaxDesc), vp, i32, vp, vp]
+    lib.metro_back_project.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp, vp]
     lib.metro_conv2d.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.metro_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     lib.metro_profile.argtypes = [vp, vp, i32, vp, vp, C.c_char_p, C.c_size_t, C.POINTER(i32)]

@@ -164,6 +164,44 @@ def run_to_orig_cam(tf, poses, rot, joint_info):
     return V.to_orig_cam(tf.convert_to_tensor(poses), tf.convert_to_tensor(rot), joint_info).value
 
 
+def run_true_root_depth(tf, flags, tfu, coords01, inv_intrinsics, root_z, stride, proc_side=256, centered_stride=True):
+    """The 'true-root-depth' branch of build_inference_model (src/model/volumetric.py:190-198) followed by root_relative
+    (:203): image coordinates -> homogeneous -> inverse intrinsics -> back_project with the given root depth."""
+    import model.volumetric as V
+    import tfu3d
+    flags.stride_test, flags.proc_side, flags.centered_stride = stride, proc_side, centered_stride
+    coords3d = tf.convert_to_tensor(coords01)
+    inv_k = tf.convert_to_tensor(inv_intrinsics)
+    coords2d_pred = coords3d[..., :2]
+    im_pred2d = V.heatmap_to_image(coords2d_pred, tfu.TEST)
+    im_pred2d_homog = V.to_homogeneous_coords(im_pred2d)
+    camcoords2d_homog = V.matmul_joint_coords(inv_k, im_pred2d_homog)
+    delta_z_pred = (coords3d[..., 2] - coords3d[:, -1:, 2]) * flags.box_size_mm
+    pred = V.back_project(camcoords2d_homog, delta_z_pred, tf.convert_to_tensor(root_z))
+    return pred.value, tfu3d.root_relative(pred).value
+
+
+def run_heatmap_pred_z(tf, flags, tfu, head_nhwc, joint_info):
+    """t.heatmap_pred_z = reduce_sum(softmaxed, axis=[2, 3]) (src/model/volumetric.py:165): the depth marginal [N, J, D]."""
+    import model.volumetric as V
+    tfu.set_data_format('NCHW')
+    net_output = tfu.nhwc_to_std(tf.convert_to_tensor(head_nhwc, dtype=tf.float32))
+    softmaxed, _ = V.net_output_to_heatmap_and_coords(net_output, joint_info)
+    return tf.reduce_sum(softmaxed, axis=[2, 3]).value
+
+
+def synth_inv_intrinsics(n, seed, proc_side=256):
+    """Inverse intrinsic matrices of crop cameras: focal length of a few hundred pixels, principal point near the centre."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        f = rng.uniform(250.0, 900.0)
+        k = np.array([[f, 0.0, proc_side / 2 + rng.uniform(-4, 4)], [0.0, f * rng.uniform(0.98, 1.02), proc_side / 2 + rng.uniform(-4, 4)],
+                      [0.0, 0.0, 1.0]])
+        out.append(np.linalg.inv(k))
+    return np.stack(out)
+
+
 def synth_rotations(n, seed):
     """n 3x3 matrices: proper rotations, every second one composed with a horizontal flip (det < 0), which is
     what `rot_to_orig_cam = ex.camera.R @ cam.R.T` holds after cam.horizontal_flip() (data_loading.py:80-83,110)."""
@@ -213,6 +251,19 @@ def main(only=None):
         rot = synth_rotations(n, 11 + ji.n_joints)
         post[f'{ds}_orig_cam'] = run_to_orig_cam(tf, poses, rot, ji)
         post[f'{ds}_meta'] = np.array([n, ji.n_joints, 7 + ji.n_joints, 11 + ji.n_joints])
+        # absolute-scale variant 'true-root-depth' (volumetric.py:190-198): seeded heatmap coordinates, cameras, depths
+        rng = np.random.RandomState(23 + ji.n_joints)
+        coords01 = rng.rand(n, ji.n_joints, 3)
+        inv_k = synth_inv_intrinsics(n, 29 + ji.n_joints)
+        root_z = rng.uniform(2000.0, 6000.0, n)
+        for stride in (4, 16, 32):
+            absolute, rootrel = run_true_root_depth(tf, flags, tfu, coords01, inv_k, root_z, stride)
+            post[f'{ds}_trd_abs_s{stride}'], post[f'{ds}_trd_rel_s{stride}'] = absolute, rootrel
+    # depth marginal of the softmaxed heatmap, t.heatmap_pred_z (volumetric.py:165)
+    for name, side, j in (('A', 8, 17), ('C', 32, 19)):
+        head = synth_head(2, side, j, seed=300 + side + j)
+        post[f'pred_z_{name}'] = run_heatmap_pred_z(tf, flags, tfu, head, FixedJoints(j))
+        post[f'pred_z_{name}_meta'] = np.array([2, side, j, 300 + side + j])
     np.savez_compressed(os.path.join(out_dir, 'post.npz'), **post)
     if only == 'post':
         return

@@ -302,3 +302,29 @@ def to_orig_cam_ref(poses: np.ndarray, rot_to_orig_cam: np.ndarray, mirror_mappi
     y = np.einsum('bij,bcj->bci', r, x)
     keep = np.linalg.det(r) > 0
     return np.where(keep[:, None, None], y, y[:, list(mirror_mapping)])
+
+
+def true_root_depth_ref(coords01: np.ndarray, inv_intrinsics: np.ndarray, root_z: np.ndarray, stride: int,
+                        centered_stride: bool = True, proc_side: int = 256, box_size_mm: float = BOX_SIZE_MM) -> np.ndarray:
+    """Absolute-scale variant 'true-root-depth' of the evaluation graph (src/model/volumetric.py:190-198): the 2D part of
+    the heatmap coordinates goes to image pixels (heatmap_to_image, :288-295), to homogeneous coordinates (:225-226) and
+    through the inverse intrinsics (matmul_joint_coords, :221-222); the depth relative to the root joint (the LAST one)
+    is scaled to millimetres; back_project (:285) multiplies the rays by (relative depth + true root depth).
+    Returns absolute camera-frame coordinates [N, J, 3] (float64)."""
+    c = np.asarray(coords01, np.float64)
+    last = proc_side - 1
+    lrc = last - (last % stride) - 1
+    im = c[..., :2] * lrc + (stride // 2 if centered_stride else 0)
+    homog = np.concatenate([im, np.ones_like(im[..., :1])], axis=-1)
+    rays = np.einsum('bij,bcj->bci', np.asarray(inv_intrinsics, np.float64), homog)
+    dz = (c[..., 2] - c[:, -1:, 2]) * box_size_mm
+    return rays * (dz + np.asarray(root_z, np.float64)[:, None])[..., None]
+
+
+def heatmap_pred_z_ref(head_nhwc: np.ndarray, n_joints: int) -> np.ndarray:
+    """t.heatmap_pred_z (src/model/volumetric.py:165): the softmax over (H, W, D) summed over H and W -> [N, J, D]."""
+    x = np.asarray(head_nhwc, np.float64)
+    n, h, w, c = x.shape
+    d = c // n_joints
+    t = x.reshape(n, h, w, d, n_joints).transpose(0, 4, 1, 2, 3)            # [N, J, H, W, D]
+    return softmax_ref(t, axis=(2, 3, 4)).sum(axis=(2, 3))

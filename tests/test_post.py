@@ -103,3 +103,109 @@ def test_round_trip_property():
     y = to_orig_cam_ref(x, rot, mm)
     back = to_orig_cam_ref(y, np.transpose(rot, (0, 2, 1)), mm)
     assert np.abs(back - x).max() < 1e-9
+
+
+# ---- absolute-scale variant and the depth marginal (second half) ------------------------------
+
+def _trd_inputs(ds):
+    import oracle.gen_golden as G                     # the seeded input generators only (no reference needed)
+    j = {'h36m': 17, 'merged': 53}[ds]
+    rng = np.random.RandomState(23 + j)
+    coords01 = rng.rand(6, j, 3)
+    return coords01, G.synth_inv_intrinsics(6, 29 + j), rng.uniform(2000.0, 6000.0, 6)
+
+
+@pytest.mark.parametrize('ds', ['h36m', 'merged'])
+def test_true_root_depth_oracle_matches_reference_code(ds):
+    from oracle.metro_oracle import true_root_depth_ref
+    g = np.load(os.path.join(GOLD, 'post.npz'))
+    c, k, z = _trd_inputs(ds)
+    for stride in (4, 16, 32):
+        a = true_root_depth_ref(c, k, z, stride)
+        assert np.abs(a - g[f'{ds}_trd_abs_s{stride}']).max() < 1e-9
+        assert np.abs((a - a[:, -1:]) - g[f'{ds}_trd_rel_s{stride}']).max() < 1e-9
+
+
+def test_heatmap_pred_z_oracle_matches_reference_code():
+    from oracle.metro_oracle import heatmap_pred_z_ref
+    from metro_pose3d_b200.weights import synth_head
+    g = np.load(os.path.join(GOLD, 'post.npz'))
+    for name in ('A', 'C'):
+        n, side, j, seed = (int(v) for v in g[f'pred_z_{name}_meta'])
+        got = heatmap_pred_z_ref(synth_head(n, side, j, seed=seed), j)
+        assert np.abs(got - g[f'pred_z_{name}']).max() < 1e-12
+        assert np.allclose(got.sum(-1), 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('ds', ['h36m', 'merged'])
+def test_cuda_back_project(ds):
+    """metro_back_project against the reference-code vectors: 1e-3 mm on identical (float32) inputs, 2e-3 mm against the
+    float64-input vectors (the float32 rounding of the inputs alone moves a 6 m ray by up to ~5e-4 mm)."""
+    import torch
+    from metro_pose3d_b200.inference import back_project
+    from oracle.metro_oracle import true_root_depth_ref
+    g = np.load(os.path.join(GOLD, 'post.npz'))
+    c, k, z = (a.astype(np.float32) for a in _trd_inputs(ds))
+    for stride in (4, 16, 32):
+        got = back_project(torch.from_numpy(c).cuda(), torch.from_numpy(k).cuda(), torch.from_numpy(z).cuda(), stride).cpu().numpy()
+        assert np.abs(got - true_root_depth_ref(c, k, z, stride)).max() < 1e-3
+        assert np.abs(got - g[f'{ds}_trd_abs_s{stride}']).max() < 2e-3
+
+
+@pytest.mark.gpu
+def test_cuda_coords_and_depth_marginal():
+    """The decode's second fetch (heatmap coordinates in [0,1]) against the reference-code vectors of tests/golden/decode.npz
+    and the depth marginal t.heatmap_pred_z against post.npz."""
+    import torch
+    from metro_pose3d_b200.inference import SoftArgmax
+    from metro_pose3d_b200.joints import export_permutation
+    from metro_pose3d_b200.weights import synth_head
+    d = np.load(os.path.join(GOLD, 'decode.npz'))
+    for case, ds in (('A', 'h36m'), ('B', 'h36m'), ('C', 'coco19'), ('E', 'coco19')):
+        n, side, stride, j, seed = (int(v) for v in d[f'{case}_meta'])
+        op = SoftArgmax(side, j, stride, export_permutation(ds))
+        poses, c01 = op.coords(torch.from_numpy(synth_head(n, side, j, seed=seed)).cuda())
+        assert np.abs(c01.cpu().numpy() - d[f'{case}_coords01']).max() < 5e-7          # 1e-3 mm / 2200 mm
+        assert np.abs(poses.cpu().numpy() - d[f'{case}_poses']).max() < 1e-3
+    g = np.load(os.path.join(GOLD, 'post.npz'))
+    for name in ('A', 'C'):
+        n, side, j, seed = (int(v) for v in g[f'pred_z_{name}_meta'])
+        op = SoftArgmax(side, j, 256 // side, list(range(j)))
+        got = op.heatmap_z(torch.from_numpy(synth_head(n, side, j, seed=seed)).cuda()).cpu().numpy()
+        assert np.abs(got - g[f'pred_z_{name}']).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_cuda_network_coords_feed_back_projection():
+    """images -> metro_infer_coords -> metro_back_project: the 'true-root-depth' evaluation path end to end, strict
+    precision against the float64 oracle (1e-3 mm), and the tensor-core path's coords consistent with its poses."""
+    import torch
+    from metro_pose3d_b200.inference import MetroModel, back_project
+    from metro_pose3d_b200.joints import export_permutation
+    from metro_pose3d_b200.spec import NetSpec
+    from metro_pose3d_b200.weights import synth_images, synth_weights
+    from oracle.metro_oracle import OracleNet, decode_ref, true_root_depth_ref
+    import oracle.gen_golden as G
+    spec = NetSpec('resnet_v2_50', 32, 17)
+    w = synth_weights(spec, 0)
+    perm = export_permutation('h36m')
+    img = synth_images(2, seed=31)
+    x = torch.from_numpy(img).cuda()
+    head = OracleNet(spec, w, perm, 'fp64').forward_head(img)
+    want_c = decode_ref(head, 17, 32, perm, return_coords01=True)
+    inv_k = G.synth_inv_intrinsics(2, 5).astype(np.float32)
+    z = np.array([3000.0, 4500.0], np.float32)
+    strict = MetroModel('resnet_v2_50', 32, 'h36m', weights=w, max_batch=2, precision='strict')
+    poses, c01 = strict.infer_coords(x)
+    assert np.abs(c01.cpu().numpy() - want_c).max() < 5e-7
+    absolute = back_project(c01, torch.from_numpy(inv_k).cuda(), torch.from_numpy(z).cuda(), 32).cpu().numpy()
+    assert np.abs(absolute - true_root_depth_ref(want_c, inv_k, z, 32)).max() < 2e-3
+    fast = MetroModel('resnet_v2_50', 32, 'h36m', weights=w, max_batch=2)
+    p2, c2 = fast.infer_coords(x)
+    assert np.array_equal(p2.cpu().numpy(), fast.infer(x).cpu().numpy())
+    # the coords are the poses before metric scaling / root subtraction / permutation (volumetric.py:303-306)
+    c2 = c2.cpu().numpy().astype(np.float64)
+    lrc = 255 - (255 % 32) - 1
+    metric = np.concatenate([c2[..., :2] * lrc * 2200.0 / 256, c2[..., 2:] * 2200.0], -1)
+    assert np.abs((metric - metric[:, -1:])[:, perm] - p2.cpu().numpy()).max() < 2e-3
