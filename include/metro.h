@@ -183,6 +183,20 @@ metro_status metro_back_project(const float *coords01_dev, const float *inv_intr
                                 int32_t n, int32_t n_joints, int32_t stride, int32_t centered_stride, int32_t proc_side,
                                 float box_size_mm, float *out_dev, void *stream);
 
+/* ---- pre-path: crop extraction.  Replaces cameralib.reproject_image_fast (src/cameralib.py:406-429,
+ *      called from src/data/data_loading.py:93): a homography warp of a full frame to a side x side crop with OpenCV's
+ *      fixed-point bilinear cv2.remap(INTER_LINEAR, BORDER_CONSTANT) arithmetic, bit for bit.  Each source names a uint8 RGB
+ *      frame in device memory and the float32 row-major homography that maps OUTPUT pixel (x, y, 1) to frame coordinates
+ *      (np.linalg.solve(new_matrix.T, old_matrix.T).T, cameralib.py:411-413).  crops_u8_dev: uint8 [n, side, side, 3], the
+ *      input layout of metro_infer_u8.  `srcs` is a HOST array; it travels in kernel parameters (no allocation, async). ---- */
+typedef struct metro_crop_src {
+  const uint8_t *frame_dev;   /* uint8 [height, width, 3], rows row_stride_bytes apart                       */
+  int32_t height, width, row_stride_bytes;
+  float homography[9];
+} metro_crop_src;
+metro_status metro_extract_crops(const metro_crop_src *srcs, int32_t n, int32_t side, int32_t border_value,
+                                 uint8_t *crops_u8_dev, void *stream);
+
 /* ---- post-path: back into the original camera frame.  Replaces to_orig_cam
  *      (volumetric.py:277-282): out[b,c,:] = R[b] @ poses[b,c',:], c' = c where det(R[b]) > 0, else
  *      mirror_mapping[c] (the crop was flipped, data_loading.py:80-83; JointInfo.mirror_mapping,

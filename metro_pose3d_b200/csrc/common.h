@@ -73,6 +73,7 @@ metro_status softargmax_launch(const SoftargmaxLaunch &L, cudaStream_t stream);
 // ---- post-path transforms ---------------------------------------------------------------------------
 metro_status to_orig_cam_launch(const float *poses, const float *rot, const int32_t *mirror, int n, int j, float *out,
                                 cudaStream_t stream);
+metro_status extract_crops_launch(const metro_crop_src *srcs, int n, int side, int border, unsigned char *out, cudaStream_t stream);
 metro_status back_project_launch(const float *coords01, const float *inv_k, const float *z_off, int n, int j, double lrc,
                                  double add_xy, double box, float *out, cudaStream_t stream);
 metro_status heatmap_z_launch(const void *head, bool f16, int n, int side, int j, int depth, float *out, cudaStream_t stream);

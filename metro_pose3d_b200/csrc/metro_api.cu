@@ -947,6 +947,21 @@ metro_status infer_host(metro_handle *h, const void *images_host_v, bool u8, int
 }
 }  // namespace
 
+metro_status metro_extract_crops(const metro_crop_src *srcs, int32_t n, int32_t side, int32_t border_value, uint8_t *crops_u8_dev,
+                                 void *stream) {
+  if (n < 0 || side <= 0 || side > 4096) return fail(METRO_ERR_VALUE, "extract_crops: bad batch / side");
+  if (border_value < 0 || border_value > 255) return fail(METRO_ERR_VALUE, "extract_crops: border value must be a byte");
+  if (n == 0) return METRO_OK;
+  if (!srcs || !crops_u8_dev) return fail(METRO_ERR_VALUE, "extract_crops: null argument");
+  for (int i = 0; i < n; ++i) {
+    const metro_crop_src &s = srcs[i];
+    if (!s.frame_dev || s.height <= 0 || s.width <= 0 || s.row_stride_bytes < 3 * s.width)
+      return fail(METRO_ERR_VALUE, "extract_crops: source %d is not a valid uint8 RGB frame", i);
+    if (s.height > 32767 || s.width > 32767) return fail(METRO_ERR_VALUE, "extract_crops: frames above 32767 pixels a side are not supported (cv2.remap's int16 coordinates)");
+  }
+  return extract_crops_launch(srcs, n, side, border_value, crops_u8_dev, static_cast<cudaStream_t>(stream));
+}
+
 metro_status metro_to_orig_cam(const float *poses_dev, const float *rot_dev, const int32_t *mirror_mapping, int32_t n,
                                int32_t n_joints, float *out_dev, void *stream) {
   if (n < 0) return fail(METRO_ERR_VALUE, "to_orig_cam: negative batch");

@@ -347,6 +347,46 @@ def back_project(coords01, inv_intrinsics, z_offset, stride: int, centered_strid
     return out
 
 
+def crop_homography(old_intrinsics, old_r, new_intrinsics, new_r) -> np.ndarray:
+    """The homography of ``cameralib.reproject_image_fast`` (src/cameralib.py:411-413): maps a pixel of the NEW
+    (crop) camera to the pixel of the OLD (frame) camera that sees the same ray; both cameras share their centre."""
+    old_matrix = np.asarray(old_intrinsics, np.float64) @ np.asarray(old_r, np.float64)
+    new_matrix = np.asarray(new_intrinsics, np.float64) @ np.asarray(new_r, np.float64)
+    return np.linalg.solve(new_matrix.T, old_matrix.T).T.astype(np.float32)
+
+
+def extract_crops(frames, homographies, side: int = 256, border_value: int = 0, out=None):
+    """``reproject_image_fast`` (src/cameralib.py:406-429) on the GPU: ``frames`` is one CUDA uint8 ``[H, W, 3]`` tensor
+    (every crop comes from it) or a sequence of such tensors, one per crop; ``homographies`` float32 ``[n, 3, 3]`` (host).
+    Returns CUDA uint8 ``[n, side, side, 3]`` crops -- the input of ``MetroModel.infer`` -- with cv2.remap's exact
+    fixed-point bilinear arithmetic."""
+    torch = _torch()
+    hs = np.ascontiguousarray(np.asarray(homographies, dtype=np.float32).reshape(-1, 9))
+    n = hs.shape[0]
+    single = hasattr(frames, 'dim')
+    if not single and len(frames) != n:
+        raise ValueError(f'{len(frames)} frames for {n} homographies')
+    srcs = (_lib.CropSrc * max(n, 1))()
+    keep = []
+    for i in range(n):
+        f = frames if single else frames[i]
+        if f.dim() != 3 or f.shape[2] != 3 or f.dtype != torch.uint8 or not f.is_cuda or f.stride(2) != 1 or f.stride(1) != 3:
+            raise ValueError('frames must be CUDA uint8 [H, W, 3] tensors with packed pixels')
+        keep.append(f)
+        srcs[i].frame_dev = f.data_ptr()
+        srcs[i].height, srcs[i].width, srcs[i].row_stride_bytes = f.shape[0], f.shape[1], f.stride(0)
+        for k in range(9):
+            srcs[i].homography[k] = float(hs[i, k])
+    dev = (frames if single else frames[0]).device if n else torch.device('cuda')
+    if out is None:
+        out = torch.empty((n, side, side, 3), dtype=torch.uint8, device=dev)
+    elif tuple(out.shape) != (n, side, side, 3) or out.dtype != torch.uint8 or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError(f'out must be a contiguous CUDA uint8 [{n},{side},{side},3] tensor')
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.load().metro_extract_crops(srcs, n, side, border_value, out.data_ptr(), stream))
+    return out
+
+
 def conv2d(x, w_hwio: np.ndarray, scale: np.ndarray, shift: np.ndarray, stride: int = 1, rate: int = 1,
            pad_lo: Optional[int] = None, relu: bool = False, out_dtype: str = 'f16', res=None, res_stride: int = 0,
            res_shift: int = 0, x2=None, w2: Optional[np.ndarray] = None, scale2=None, shift2=None):

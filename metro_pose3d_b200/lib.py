@@ -23,7 +23,7 @@ EXPORTS = [
     'metro_last_error', 'metro_version', 'metro_blob_floats', 'metro_plan_describe', 'metro_create',
     'metro_destroy', 'metro_workspace_bytes', 'metro_get_joint_info', 'metro_infer', 'metro_infer_host', 'metro_infer_u8', 'metro_infer_host_u8', 'metro_to_orig_cam',
     'metro_softargmax_workspace_bytes', 'metro_softargmax', 'metro_softargmax_coords', 'metro_infer_coords', 'metro_heatmap_z',
-    'metro_back_project', 'metro_conv2d', 'metro_debug_read',
+    'metro_back_project', 'metro_extract_crops', 'metro_conv2d', 'metro_debug_read',
     'metro_profile', 'metro_launch_count', 'metro_graph_stats',
 ]
 
@@ -53,6 +53,11 @@ class ConvDesc(C.Structure):
         ('stride', C.c_int32), ('rate', C.c_int32), ('pad_lo', C.c_int32), ('relu', C.c_int32),
         ('out_dtype', C.c_int32), ('res_stride', C.c_int32), ('res_shift', C.c_int32), ('cin2', C.c_int32),
     ]
+
+
+class CropSrc(C.Structure):
+    _fields_ = [('frame_dev', C.c_void_p), ('height', C.c_int32), ('width', C.c_int32), ('row_stride_bytes', C.c_int32),
+                ('homography', C.c_float * 9)]
 
 
 class MetroError(RuntimeError):
@@ -103,6 +108,7 @@ def load() -> C.CDLL:
     lib.metro_infer_coords.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.metro_heatmap_z.argtypes = [C.POINTER(SoftargmaxDesc), vp, i32, vp, vp]
     lib.metro_back_project.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp, vp]
+    lib.metro_extract_crops.argtypes = [C.POINTER(CropSrc), i32, i32, i32, vp, vp]
     lib.metro_conv2d.argtypes = [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.metro_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     lib.metro_profile.argtypes = [vp, vp, i32, vp, vp, C.c_char_p, C.c_size_t, C.POINTER(i32)]

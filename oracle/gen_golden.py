@@ -202,6 +202,50 @@ def synth_inv_intrinsics(n, seed, proc_side=256):
     return np.stack(out)
 
 
+def synth_frame(h, w, seed):
+    """A uint8 RGB frame: smooth gradients + blocks + noise, so that interpolation, borders and rounding all matter."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[:h, :w]
+    base = np.stack([(xx * 255 // max(w - 1, 1)), (yy * 255 // max(h - 1, 1)), ((xx // 16 + yy // 16) % 2) * 200], -1)
+    return np.clip(base + rng.randint(-40, 41, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def synth_crop_cameras(n, h, w, seed, side):
+    """(intrinsics_old, R_old, intrinsics_new, R_new) per crop: a frame camera and a crop camera that was turned towards a
+    point of the frame, zoomed and rolled -- what load_and_transform3d builds (data_loading.py:43-58), some crops reaching
+    beyond the frame so that the constant border takes part."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        f = rng.uniform(0.8, 1.4) * w
+        k_old = np.array([[f, 0, w / 2 + rng.uniform(-8, 8)], [0, f, h / 2 + rng.uniform(-8, 8)], [0, 0, 1.0]])
+        q, r = np.linalg.qr(rng.randn(3, 3))
+        r_old = q * np.sign(np.diag(r))
+        if np.linalg.det(r_old) < 0:
+            r_old[:, 0] = -r_old[:, 0]
+        ang = rng.uniform(-0.35, 0.35, 3)
+        cx, sx = np.cos(ang[0]), np.sin(ang[0]); cy, sy = np.cos(ang[1]), np.sin(ang[1]); cz, sz = np.cos(ang[2]), np.sin(ang[2])
+        turn = (np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+                np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]))
+        fz = f * rng.uniform(0.5, 2.5) * side / w
+        k_new = np.array([[fz, 0, (side - 1) / 2], [0, fz, (side - 1) / 2], [0, 0, 1.0]])
+        out.append((k_old, r_old, k_new, turn @ r_old))
+    return out
+
+
+def run_reproject_image_fast(frame, cams, side):
+    """The reference's own cameralib.reproject_image_fast (src/cameralib.py:406-429), cv2.remap included; cameralib's
+    unused imports that are absent here (transforms3d) are stubbed."""
+    sys.modules.setdefault('transforms3d', types.ModuleType('transforms3d'))
+    import cameralib
+    res = []
+    for k_old, r_old, k_new, r_new in cams:
+        old = types.SimpleNamespace(intrinsic_matrix=k_old, R=r_old)
+        new = types.SimpleNamespace(intrinsic_matrix=k_new, R=r_new)
+        res.append(cameralib.reproject_image_fast(frame, old, new, (side, side)))
+    return np.stack(res)
+
+
 def synth_rotations(n, seed):
     """n 3x3 matrices: proper rotations, every second one composed with a horizontal flip (det < 0), which is
     what `rot_to_orig_cam = ex.camera.R @ cam.R.T` holds after cam.horizontal_flip() (data_loading.py:80-83,110)."""
@@ -265,6 +309,25 @@ def main(only=None):
         post[f'pred_z_{name}'] = run_heatmap_pred_z(tf, flags, tfu, head, FixedJoints(j))
         post[f'pred_z_{name}_meta'] = np.array([2, side, j, 300 + side + j])
     np.savez_compressed(os.path.join(out_dir, 'post.npz'), **post)
+
+    # ---- pre-path: crop extraction, the reference's reproject_image_fast --------------------------
+    from oracle.crop_oracle import crop_homography, reproject_image_fast_ref
+    crops = {}
+    for name, h, w, side, n, seed in (('vga', 480, 640, 96, 5, 41), ('tall', 700, 380, 64, 4, 43)):
+        frame = synth_frame(h, w, seed)
+        cams = synth_crop_cameras(n, h, w, seed + 1, side)
+        ref = run_reproject_image_fast(frame, cams, side)
+        hs = np.stack([crop_homography(*c) for c in cams])
+        mine = np.stack([reproject_image_fast_ref(frame, hm, side, side) for hm in hs])
+        crops[f'{name}_crops'] = ref
+        crops[f'{name}_homographies'] = hs
+        crops[f'{name}_meta'] = np.array([h, w, side, n, seed])
+        # pixels where the reference's BLAS-ordered float32 coordinates round to another 1/32-pixel cell than the fixed
+        # evaluation order of oracle/crop_oracle.py (documented there); recorded so that the GPU test can hold the rest exact
+        crops[f'{name}_blas_mismatch'] = np.argwhere(np.any(ref != mine, axis=-1))
+        print(f'crops {name}: {ref.shape}, border pixels {(ref.sum(-1) == 0).mean():.2%}, '
+              f'pixels differing from the fixed-order oracle: {len(crops[f"{name}_blas_mismatch"])} of {ref[..., 0].size}', flush=True)
+    np.savez_compressed(os.path.join(out_dir, 'crops.npz'), **crops)
     if only == 'post':
         return
 
