@@ -44,3 +44,14 @@ if __name__ == '__main__':
         net(n=int(sys.argv[2]) if len(sys.argv) > 2 else 256, steps=int(sys.argv[3]) if len(sys.argv) > 3 else 2)
     elif what == 'net_d':
         net('resnet_v2_101', 16, 'coco19')
+    elif what == 'net_cfg':            # net_cfg <config> <batch> <steps>
+        from metro_pose3d_b200.spec import CONFIGS
+        arch, stride, ds, _, _ = CONFIGS[sys.argv[2]]
+        net(arch, stride, ds, n=int(sys.argv[3]), steps=int(sys.argv[4]) if len(sys.argv) > 4 else 2)
+    elif what == 'roles':              # METRO_ROLE_PROF=1: per-launch times + role timers of one config-B step
+        from metro_pose3d_b200.inference import MetroModel
+        m = MetroModel('resnet_v2_50', 16, 'h36m', max_batch=256)
+        x = torch.rand((256, 256, 256, 3), device='cuda')
+        m.infer(x); torch.cuda.synchronize()
+        for name, ms in m.profile(x):
+            print(f'{name:50s} {ms*1e3:9.1f} us')
