@@ -120,6 +120,32 @@ def cpu_oracle_rate(spec, weights, dataset, n_sample, threads, repeats=1):
     return n_sample / dt, dt
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pinned staging buffers should live on the socket the GPU hangs off (round-1 finding: eight ranks pinning on one
+    node share that node's memory bandwidth).  Binds this process to the CPUs of the GPU's NUMA node before any pinned
+    allocation; returns a short description for the JSON line (None if the platform exposes no topology)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), 'pci_domain_id', 0)
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f'/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node'
+        node = int(open(path).read().strip())
+        if node < 0:
+            return 'numa_node=-1 (single node)'
+        cpus = open(f'/sys/devices/system/node/node{node}/cpulist').read().strip()
+        ids = set()
+        for part in cpus.split(','):
+            a, _, b = part.partition('-')
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return f'numa_node={node} cpus={cpus}'
+    except Exception as e:           # no sysfs / no permission: leave the affinity alone
+        return None
+
+
 def make_config(cfg_name, arch, stride, j, per_gpu, world):
     """The workload description both arms print (the driver compares them)."""
     return {'workload': f'config {cfg_name}: {arch} stride_{stride} {j} joints, batch {per_gpu}/GPU',
@@ -201,6 +227,7 @@ def main():
         raise SystemExit('bench.py needs a B200: the product path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     hbm_peak, tf_burst, tf_sust, peak_src = load_peaks()
@@ -331,11 +358,12 @@ def main():
     conv_ms_launches = sum(v for k, v in acc.items() if k not in non_gemm)
     # the same launches inside the real step: whole-step device time (the timed region above) minus the other kernels
     conv_ms_step = ms_local - sum(acc[k] for k in non_gemm if k in acc)
-    # ONE fixed method: the sum of the per-launch device times (CUDA events between launches, minimum over the
-    # repetitions).  It serialises the launches, so it does not see the overlap of consecutive kernels in the real
-    # step; the step-derived figure is carried as a named extra, never substituted.
+    # ONE fixed method: the sum of the per-launch device times, each launch timed INSIDE the real pipelined step by
+    # device-side stamps (earliest CTA start after its dependency wait -> latest CTA end, %globaltimer; metro_profile),
+    # minimum over the repetitions.  (CUDA events between launches, the round-1 method, serialise the launches and add a
+    # launch latency to each: their sum exceeded the whole step.)  The step-derived figures are named extras.
     conv_ms = conv_ms_launches
-    conv_timing = 'sum of per-launch event times (min over %d repetitions)' % reps
+    conv_timing = 'sum of per-launch device time stamps inside the pipelined step (min over %d repetitions)' % reps
     gemm_convs = [c for c in spec.convs if c.name != 'conv1']
     # algorithmic FLOPs: 2*Ho*Wo*Cout*Cin*k^2 per conv per crop; the root conv1 has its own fused kernel
     gemm_flops = sum(c.flops for c in gemm_convs) * n
@@ -348,13 +376,14 @@ def main():
             traffic = json.load(open(tpath)).get('conv_gemm_dram_bytes_per_step')
         except Exception:
             traffic = None
-    roofline = {'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all %d launches)' % len([k for k in acc if k not in non_gemm]),
+    roofline = {'kernel': 'conv_gemm_kernel + conv_chain_kernel (tcgen05 implicit GEMM; all %d convolution launches of a step)' % len([k for k in acc if k not in non_gemm]),
                 'bound': 'tensor', 'achieved': achieved_tf, 'peak': tf_sust, 'unit': 'TFLOP/s',
                 'frac': achieved_tf / tf_sust, 'traffic': traffic, 'peak_source': f'{peak_src} bf16 sustained',
                 'algorithmic_flops_per_step': gemm_flops,
                 'ms_per_step': conv_ms, 'timing': conv_timing, 'ms_sum_of_launches': conv_ms_launches,
                 'extra_ms_step_minus_others': conv_ms_step,
                 'extra_frac_step_minus_others': gemm_flops / (conv_ms_step * 1e-3) / 1e12 / tf_sust,
+                'extra_frac_conv_flops_over_whole_step': gemm_flops / (ms_local * 1e-3) / 1e12 / tf_sust,
                 'other_ms': {k: acc[k] for k in non_gemm if k in acc}}
     if args.layers:
         flops = {c.name: c.flops for c in spec.convs}
@@ -426,6 +455,7 @@ def main():
                     'arithmetic': 'f16 operands (the reference default, src/options.py:73), f32 accumulate, f32 head and decode',
                     'head_dtype': args.head_dtype, 'gflop_per_crop': spec.flops_per_crop / 1e9,
                     'tensor_frac_whole_step': spec.flops_per_crop * n / (ms_local * 1e-3) / 1e12 / tf_sust,
+                    'host_numa_binding': numa,
                     'extended_region': {'steps': ext_steps, 'ms_per_step': ms_ext, 'clocks': clocks_ext}},
         'e2e': e2e, 'e2e_u8': e2e_u8, 'gpu_launches': model.launch_count(n) * args.steps,
         'roofline': roofline, 'roofline_softargmax': roofline_sam, 'cpu_baseline': cpu, 'clocks': clocks,

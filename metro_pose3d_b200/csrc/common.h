@@ -65,6 +65,7 @@ struct SoftargmaxLaunch {
   // dataflow (ptx.cuh): wait for the crop's counter of the logits layer instead of for the whole previous grid
   const unsigned int *dep_flags;   // indexed by crop of THIS launch (already offset), or null
   unsigned int dep_expected;
+  unsigned long long *tstamp;      // optional [2]: earliest CTA start / latest CTA end (%globaltimer ns), metro_profile
 };
 metro_status softargmax_plan(const metro_softargmax_desc &d, int n, SoftargmaxLaunch &L);
 size_t softargmax_workspace_bytes(const SoftargmaxLaunch &L);

@@ -114,6 +114,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
   const uint32_t tmem_base = *s_tmem;
   if (!p.dep_flags) ptx::griddep_wait();
   ptx::griddep_launch_dependents();
+  ptx::stamp_begin(p.tstamp);             // after the grid-wide dependency (if any): the prologue above overlapped the previous kernel
   const int n_end = p.m_total / (p.ho * p.wo);
   // role timers (METRO_ROLE_PROF, same slots as conv_gemm.cu; 12 = epilogue waits for the operand buffer, 13 = MMA
   // waits for the pre-activation, 14 = MMA waits for the conv1 accumulator, 15 = weight producer waits for a slot)
@@ -422,6 +423,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
     ptx::flag_signal(p.sig_done);
   }
   if (prof && threadIdx.x == 0) pr[0] = clock64() - t_start;
+  ptx::stamp_end(p.tstamp);
 }
 
 template <int BN1>

@@ -156,6 +156,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
   // first tiles start while the previous layer's last wave is still running.)
   if (!p.dep_flags) ptx::griddep_wait();
   ptx::griddep_launch_dependents();
+  ptx::stamp_begin(p.tstamp);             // after the grid-wide dependency (if any): the prologue above overlapped the previous kernel
   const int n_end = p.m_total / (p.ho * p.wo);       // one past the last crop of this call's slice
 
   if (warp == 0 || warp == 3) {
@@ -643,6 +644,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXform ? kThreadsXfo
     ptx::flag_signal(p.sig_done);
   }
   if (prof && threadIdx.x == 0) p.prof[blockIdx.x * kPCount + kPTotal] = clock64() - t_start;
+  ptx::stamp_end(p.tstamp);
 }
 
 // ---- driver entry point -------------------------------------------------------------------------------

@@ -66,6 +66,9 @@ struct alignas(64) ConvGemmParams {
   CUtensorMap w1map;
   const float *scale1c, *shift1c;
   int cout1, off_a2;
+  // optional device time stamps of THIS launch (metro_profile): [0] = earliest CTA start, [1] = latest CTA end, in
+  // %globaltimer nanoseconds -- the kernel's duration inside the real, overlapped pipeline (no events between launches)
+  unsigned long long *tstamp;
 };
 
 struct ConvGemmLaunch {

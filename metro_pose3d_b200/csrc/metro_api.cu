@@ -242,6 +242,8 @@ struct metro_handle {
   // root: image pack -> fused conv1 + pool1 + first pre-activation
   float *d_pool_scale = nullptr, *d_pool_shift = nullptr, *d_root_bias = nullptr;
   __half *buf_packed = nullptr, *buf_root = nullptr, *d_root_w = nullptr, *pool_raw = nullptr, *pool_pre = nullptr;
+  __half *d_root_w2 = nullptr;   // version 2 of the root kernel (image pack folded in, paired conv rows)
+  int root_v2 = 1;               // METRO_ROOT_V1 switches back to img_pack + root_fused
   alignas(64) unsigned char image_map[128];
   std::vector<ConvGemmLaunch> gemms;
   void *buf_head = nullptr;
@@ -330,6 +332,10 @@ metro_status build_handle(metro_handle &h, const float *blob) {
     std::vector<__half> wp(root_packed_weight_elems());
     root_pack_weights(blob + pl.root.w_off, wp.data());
     if ((st = A.upload(&h.d_root_w, wp)) != METRO_OK) return st;
+    std::vector<__half> wp2(root2_packed_weight_elems());
+    root2_pack_weights(blob + pl.root.w_off, wp2.data());
+    if ((st = A.upload(&h.d_root_w2, wp2)) != METRO_OK) return st;
+    if (getenv("METRO_ROOT_V1")) h.root_v2 = 0;
     std::vector<float> bias(blob + pl.root.b_off, blob + pl.root.b_off + 64);
     if ((st = A.upload(&h.d_root_bias, bias)) != METRO_OK) return st;
     if (keep) {
@@ -520,6 +526,10 @@ struct Timer {
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> names;
   long long *role_prof = nullptr;   // device [launch][num_sms][8] role timers (METRO_ROLE_PROF=1)
+  // device-side stamps instead of events: [launch][2] = earliest CTA start / latest CTA end of every launch, taken
+  // inside the real pipeline (events between launches serialise it: no programmatic overlap, a launch latency each)
+  unsigned long long *stamps = nullptr;
+  unsigned long long *slot() const { return stamps ? stamps + 2 * names.size() : nullptr; }
 };
 
 // Dataflow wiring of convolution `li`: it waits on the counters of its producer (row li: the fused root for li == 0,
@@ -561,16 +571,23 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
   metro_status st;
   auto mark = [&](const char *name) {
     if (!t) return;
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
-    t->ev.push_back(e); t->names.push_back(name);
+    if (!t->stamps) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); t->ev.push_back(e); }
+    t->names.push_back(name);
   };
   (void)pl;
+  if (h->root_v2) {
+    if ((st = root_fused2_launch(images, u8, h->d_root_w2, h->d_root_bias, h->d_pool_scale, h->d_pool_shift,
+                                 h->spec.keep_activations ? h->pool_raw : nullptr, h->pool_pre, h->buf_root, n, n_base, h->num_sms,
+                                 s, t ? t->slot() : nullptr)) != METRO_OK) return st;
+    mark("conv1+pool1");
+  } else {
   if ((st = img_pack_launch(images, u8, h->buf_packed + size_t(n_base) * root_packed_image_elems(), n, s)) != METRO_OK) return st;
   mark("img_pack");
   if ((st = root_fused_launch(h->image_map, h->d_root_w, h->d_root_bias, h->d_pool_scale, h->d_pool_shift,
                               h->spec.keep_activations ? h->pool_raw : nullptr, h->pool_pre, h->buf_root, n, n_base, h->num_sms, s,
                               (t && t->role_prof) ? t->role_prof : nullptr, nullptr)) != METRO_OK) return st;
   mark("conv1+pool1");
+  }
   for (int li = 0; li < stem_gemms; ++li) {
     // the handle's launch record is never written after metro_create: the batch slice, walk direction and
     // profiling pointer of THIS call travel in the by-value kernel parameters (so a call can be captured
@@ -582,6 +599,7 @@ metro_status run_stem(metro_handle *h, const void *images, bool u8, int n, int n
     prm.prof = (t && t->role_prof) ? t->role_prof + size_t(li + 1) * h->num_sms * 16 : nullptr;
     set_dataflow(h, li, prm);
     if (prm.dep_flags && h->df_forward) prm.reverse = 0;
+    prm.tstamp = t ? t->slot() : nullptr;
     if ((st = L.chain ? conv_chain_launch(prm, h->num_sms, s) : conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
@@ -594,8 +612,8 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
   metro_status st;
   auto mark = [&](const char *name) {
     if (!t) return;
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
-    t->ev.push_back(e); t->names.push_back(name);
+    if (!t->stamps) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); t->ev.push_back(e); }
+    t->names.push_back(name);
   };
   for (size_t li = first_gemm; li < h->gemms.size(); ++li) {
     const ConvGemmLaunch &L = h->gemms[li];
@@ -607,10 +625,12 @@ metro_status run_tail(metro_handle *h, int n, int n_base, int first_gemm, float 
     // a layer that follows its producer crop by crop walks the tile list in the producer's order, so that the CTAs
     // which replace the producer's early finishers start on crops that are already complete
     if (prm.dep_flags && h->df_forward) prm.reverse = 0;
+    prm.tstamp = t ? t->slot() : nullptr;
     if ((st = L.chain ? conv_chain_launch(prm, h->num_sms, s) : conv_gemm_launch(L, prm, h->num_sms, s)) != METRO_OK) return st;
     mark(L.name.c_str());
   }
   SoftargmaxLaunch sl = h->sam;
+  sl.tstamp = t ? t->slot() : nullptr;
   if (h->dataflow && h->gemms.back().signals) {
     sl.dep_flags = h->flags + h->gemms.size() * size_t(h->max_batch) + n_base;
     sl.dep_expected = h->gemms.back().sig_expected;
@@ -660,8 +680,8 @@ metro_status run(metro_handle *h, const void *images, bool u8, int n, float *pos
   if (!images || !poses) return fail(METRO_ERR_VALUE, "null image / pose buffer");
   METRO_CUDA(cudaSetDevice(h->device));
   if (t) {
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
-    t->ev.push_back(e); t->names.push_back("start");
+    if (!t->stamps) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); t->ev.push_back(e); }
+    t->names.push_back("start");
   }
   if (h->strict) return strict_run(h->strict, images, u8, n, poses, s);
   if (t || n > h->graph_max_batch) return run_direct(h, images, u8, n, poses, s, t);
@@ -1137,7 +1157,7 @@ metro_status metro_launch_count(const metro_handle *h, int32_t n, int32_t *launc
     *launches = n > 0 ? int32_t(h->plan.n_convs() + h->plan.units.size() + 2 + 3) : 0;
     return METRO_OK;
   }
-  *launches = n > 0 ? int32_t(h->gemms.size()) + 3 : 0;   // + image pack, fused root, soft-argmax
+  *launches = n > 0 ? int32_t(h->gemms.size()) + (h->root_v2 ? 2 : 3) : 0;   // + [image pack,] fused root, soft-argmax
   return METRO_OK;
 }
 
@@ -1152,10 +1172,24 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
     METRO_CUDA(cudaMalloc(&t.role_prof, role_elems * sizeof(long long)));
     METRO_CUDA(cudaMemset(t.role_prof, 0, role_elems * sizeof(long long)));
   }
+  // default: device-side time stamps per launch inside the real pipeline; METRO_PROFILE_EVENTS=1 (or the fallback root
+  // kernel, which carries no stamps): CUDA events between launches, which serialise the launches
+  const bool use_stamps = !getenv("METRO_PROFILE_EVENTS") && h->root_v2;
+  const size_t max_launches = h->gemms.size() + 8;
+  std::vector<unsigned long long> hstamps(2 * max_launches);
+  if (use_stamps) {
+    for (size_t i = 0; i < max_launches; ++i) { hstamps[2 * i] = ~0ull; hstamps[2 * i + 1] = 0ull; }
+    METRO_CUDA(cudaMalloc(&t.stamps, hstamps.size() * sizeof(unsigned long long)));
+    METRO_CUDA(cudaMemcpy(t.stamps, hstamps.data(), hstamps.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  }
   METRO_CUDA(cudaDeviceSynchronize());
   metro_status st = run(h, images_dev, false, n, poses_dev, nullptr, &t);
   if (st != METRO_OK) return st;
   METRO_CUDA(cudaDeviceSynchronize());
+  if (use_stamps) {
+    METRO_CUDA(cudaMemcpy(hstamps.data(), t.stamps, hstamps.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(t.stamps);
+  }
   if (roles) {
     // per launch, averaged over CTAs: total | producer waits for a free stage | MMA waits for operands |
     // MMA waits for a free accumulator | epilogue waits for an accumulator | epilogue busy | store wait | tiles
@@ -1199,10 +1233,15 @@ metro_status metro_profile(metro_handle *h, const float *images_dev, int32_t n, 
     }
   }
   std::string names;
-  const int cnt = int(t.ev.size()) - 1;
+  const int cnt = int(t.names.size()) - 1;
   for (int i = 0; i < cnt; ++i) {
     float ms = 0;
-    cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]);
+    if (use_stamps) {      // launch i + 1 of the name list stamped slot i + 1
+      const unsigned long long b = hstamps[2 * (i + 1)], e = hstamps[2 * (i + 1) + 1];
+      ms = (e > b && b != ~0ull) ? float(double(e - b) * 1e-6) : 0.f;
+    } else {
+      cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]);
+    }
     if (ms_out) ms_out[i] = ms;
     names += t.names[i + 1];
     names += '\n';

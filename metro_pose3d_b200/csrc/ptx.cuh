@@ -340,6 +340,12 @@ __device__ __forceinline__ unsigned long long globaltimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void stamp_begin(unsigned long long *ts) {
+  if (ts && threadIdx.x == 0) atomicMin(ts, globaltimer());
+}
+__device__ __forceinline__ void stamp_end(unsigned long long *ts) {
+  if (ts && threadIdx.x == 0) atomicMax(ts + 1, globaltimer());
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -353,11 +353,346 @@ __global__ void __launch_bounds__(256) img_pack_kernel(const void *__restrict__ 
   reinterpret_cast<uint4 *>(out)[i] = o;
 }
 
+// =====================================================================================================================
+// Version 2 of the root: the image pack is folded into the kernel and two conv rows share one MMA.
+//
+//  * No packed image in HBM: four loader warps read the float32 (or uint8) crop rows straight from the caller's
+//    buffer, convert to fp16 (the cast of architectures.py:29; uint8: x * (1/255f), bit-identical after the cast to
+//    improc.py:56-61's division) and write the "pixel pair" rows of the layout above into a ring of 32 input rows in
+//    shared memory.  A conv row pair needs 4 new input rows; the 138 MB write + read of the packed image and one
+//    launch per step disappear.
+//  * conv rows (a, a + 1) are ONE accumulator of 128 columns: the 9 input rows 2a-3 .. 2a+5 are the K dimension
+//    (window position kpos), the B operand of position kpos holds the filters of kernel row kpos for conv row a
+//    (zero for kpos > 6) in its first 64 rows and of kernel row kpos - 2 for conv row a + 1 (zero for kpos < 2) in the
+//    other 64: 18 MMAs of N = 128 (64 cycles each) per pair instead of 28 of N = 64 (56 cycles each).
+//  * A CTA owns a band of 16 pool rows of one crop = 16 conv row pairs plus the pair above them whose odd row is the
+//    pool's halo; the epilogue is the one of version 1 with both rows of a pair coming from one accumulator.
+constexpr int kRingRows = 32;                       // input rows resident in shared memory (a pair's window is 9)
+constexpr int kPairMmas = 18;                       // 9 window positions x 2 K = 16 steps
+constexpr int kW2Bytes = kPairMmas * 4096;          // [mma][k-chunk 2][row-group 16][8 rows][16 B]
+constexpr int kPairDepth = 4;                       // pairs in flight: accumulators (4 x 128 columns) and row hand-over
+constexpr int kBand2 = 16;                          // pool rows per band
+constexpr int kLoaderWarps = 4;
+constexpr int kThreads2 = kThreads + kLoaderWarps * 32;   // 4 control + 8 epilogue + 4 loader warps
+
+struct alignas(16) Root2Params {
+  const void *images;      // [n][256][256][3] float32 or uint8, crop 0 of THIS call
+  int u8;
+  const __half *wpack;     // kW2Bytes, operand layout
+  const float *bias, *pscale, *pshift;
+  __half *raw, *pre, *conv_dbg;
+  int n, n_base;
+  long long *prof;
+  unsigned long long *tstamp;
+};
+
+constexpr int k2OffW = kRingRows * kRowBytes;                 // 67584
+constexpr int k2OffHist = k2OffW + kW2Bytes;                  // + 73728
+constexpr int k2OffBias = k2OffHist + 2 * kHistBytes;
+constexpr int k2OffBar = k2OffBias + 256;
+constexpr int k2SmemBytes = k2OffBar + 256;
+
+__global__ void __launch_bounds__(kThreads2, 1) root_fused2_kernel(const __grid_constant__ Root2Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + k2OffBar);
+  uint64_t *rfull = bars, *rempty = bars + kPairDepth, *tfull = bars + 2 * kPairDepth, *tempty = bars + 3 * kPairDepth;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 4 * kPairDepth);
+  float *s_bias = reinterpret_cast<float *>(smem + k2OffBias);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kBandsPerImg = kPoolW / kBand2;
+  const int n_bands = p.n * kBandsPerImg;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kPairDepth; ++i) {
+      ptx::mbar_init(rfull + i, kLoaderWarps); ptx::mbar_init(rempty + i, 1);
+      ptx::mbar_init(tfull + i, 1); ptx::mbar_init(tempty + i, 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(s_tmem, kPairDepth * 128);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kW2Bytes / 16; i += kThreads2)
+    reinterpret_cast<uint4 *>(smem + k2OffW)[i] = reinterpret_cast<const uint4 *>(p.wpack)[i];
+  // the ring starts zeroed: the two zero pairs in front of a row and the 2.5 behind it are never written again
+  for (int i = threadIdx.x; i < kRingRows * kRowBytes / 16; i += kThreads2) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < kC) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  ptx::griddep_wait();                            // the caller's images / whatever ran before in the stream
+  ptx::griddep_launch_dependents();
+  ptx::stamp_begin(p.tstamp);
+
+  // Pairs of a band: j = 0 .. 16, conv rows (2 p0 - 2 + 2 j, 2 p0 - 1 + 2 j); pair 0 only contributes the halo row and
+  // does not exist for the top band (the pool's zero padding).  Every role walks the same sequence.
+  if (warp >= 4 + 8) {
+    // ================================ loaders ================================
+    const int lt = threadIdx.x - (4 + 8) * 32;     // 0..127: two rows at a time, 64 threads (4 pixels each) per row
+    const int half = lt >> 6, t = lt & 63;
+    uint32_t seq = 0;                              // pairs issued so far
+    uint32_t ring = 0;                             // ring slot of the next row to write (rows are loaded in window order)
+    for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
+      const int img = band / kBandsPerImg, p0 = (band % kBandsPerImg) * kBand2;
+      const unsigned char *src = static_cast<const unsigned char *>(p.images) + size_t(img) * kSide * kSide * 3 * (p.u8 ? 1 : 4);
+      for (int j = p0 == 0 ? 1 : 0; j <= kBand2; ++j, ++seq) {
+        const int a = 2 * p0 - 2 + 2 * j;          // even conv row of the pair
+        const bool first = j == (p0 == 0 ? 1 : 0);
+        const int r_lo = first ? 2 * a - 3 : 2 * a + 2, r_hi = 2 * a + 5;     // input rows this pair adds to the ring
+        // rows overwritten now were last read by the pair 4 back (kRingRows = 32 makes that hold at a band start too)
+        if (seq >= kPairDepth) ptx::mbar_wait(rempty + seq % kPairDepth, ((seq / kPairDepth) & 1) ^ 1);
+        for (int r0 = r_lo; r0 <= r_hi; r0 += 2) {
+          const int r = r0 + half;
+          if (r <= r_hi) {
+            uint2 o[4];
+            if (r < 0 || r >= kSide) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] = make_uint2(0u, 0u);
+            } else if (p.u8) {
+              const uint32_t *q = reinterpret_cast<const uint32_t *>(src + (size_t(r) * kSide + 4 * t) * 3);
+              const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+              const unsigned char b[12] = {(unsigned char)w0, (unsigned char)(w0 >> 8), (unsigned char)(w0 >> 16), (unsigned char)(w0 >> 24),
+                                           (unsigned char)w1, (unsigned char)(w1 >> 8), (unsigned char)(w1 >> 16), (unsigned char)(w1 >> 24),
+                                           (unsigned char)w2, (unsigned char)(w2 >> 8), (unsigned char)(w2 >> 16), (unsigned char)(w2 >> 24)};
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                o[k] = make_uint2(pack2(float(b[3 * k]) * (1.0f / 255.0f), float(b[3 * k + 1]) * (1.0f / 255.0f)),
+                                  pack2(float(b[3 * k + 2]) * (1.0f / 255.0f), 0.f));
+            } else {
+              const float4 *q = reinterpret_cast<const float4 *>(src + (size_t(r) * kSide + 4 * t) * 12);
+              const float4 f0 = q[0], f1 = q[1], f2 = q[2];
+              o[0] = make_uint2(pack2(f0.x, f0.y), pack2(f0.z, 0.f));
+              o[1] = make_uint2(pack2(f0.w, f1.x), pack2(f1.y, 0.f));
+              o[2] = make_uint2(pack2(f1.z, f1.w), pack2(f2.x, 0.f));
+              o[3] = make_uint2(pack2(f2.y, f2.z), pack2(f2.w, 0.f));
+            }
+            // column c sits in pair (c + 3) / 2, half (c + 3) % 2: columns 4t .. 4t+3 are 32 contiguous bytes from 32 t + 24
+            const uint32_t slot = (ring + uint32_t(r - r_lo)) % kRingRows;
+            const uint32_t dst = ptx::smem_u32(smem) + slot * kRowBytes + 32u * t + 24u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + 8u * k), "r"(o[k].x), "r"(o[k].y) : "memory");
+          }
+        }
+        ring = (ring + uint32_t(r_hi - r_lo + 1)) % kRingRows;
+        ptx::fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(rfull + seq % kPairDepth);
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(128, 128);
+      const uint64_t db0 = make_nosw_kmajor_desc(ptx::smem_u32(smem + k2OffW), 2048, 128);
+      uint32_t seq = 0, win = 0;                   // win: ring slot of the current pair's window position 0
+      for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
+        const int p0 = (band % kBandsPerImg) * kBand2;
+        for (int j = p0 == 0 ? 1 : 0; j <= kBand2; ++j, ++seq) {
+          const bool first = j == (p0 == 0 ? 1 : 0);
+          // the window slides by 4 rows per pair; a band's first pair starts on 9 fresh rows
+          if (seq > 0) win = (win + (first ? 9u : 4u)) % kRingRows;
+          const uint32_t acc = seq % kPairDepth, ph = (seq / kPairDepth) & 1;
+          ptx::mbar_wait(tempty + acc, ph ^ 1);
+          ptx::mbar_wait(rfull + acc, ph);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int tt = 0; tt < kPairMmas; ++tt) {
+            const int kpos = tt >> 1, jp = tt & 1;
+            const uint32_t row = (win + uint32_t(kpos)) % kRingRows;
+            const uint64_t da = make_nosw_kmajor_desc(ptx::smem_u32(smem) + row * kRowBytes + jp * 32, 16, 128);
+            ptx::umma_f16(tmem_base + acc * 128, da, db0 + uint64_t(tt * (4096 >> 4)), idesc, tt != 0);
+          }
+          ptx::umma_commit(rempty + acc);
+          ptx::umma_commit(tfull + acc);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: version 1's, with the even row of a pair in accumulator columns 0..63 and the odd row in 64..127 ----
+    const int e = warp - 4, q = e & 3, hf = e >> 2;
+    const int wo = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const uint32_t hist_a = ptx::smem_u32(smem + k2OffHist);
+    const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + hf * 32;
+    const int chunk = et & 7, pw0 = et >> 3;
+    float ps[8], pf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ps[i] = p.pscale[chunk * 8 + i]; pf[i] = p.pshift[chunk * 8 + i]; }
+    __half2 odd[16];
+    float bias[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias[i] = s_bias[hf * 32 + i];
+    uint32_t seq = 0, pooled = 0;
+    auto to_half = [&](const uint32_t (&v)[32], __half2 (&h)[16], __half *dbg) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float *b = bias + 8 * j;
+        uint4 o;
+        o.x = pack2(__uint_as_float(v[8 * j + 0]) + b[0], __uint_as_float(v[8 * j + 1]) + b[1]);
+        o.y = pack2(__uint_as_float(v[8 * j + 2]) + b[2], __uint_as_float(v[8 * j + 3]) + b[3]);
+        o.z = pack2(__uint_as_float(v[8 * j + 4]) + b[4], __uint_as_float(v[8 * j + 5]) + b[5]);
+        o.w = pack2(__uint_as_float(v[8 * j + 6]) + b[6], __uint_as_float(v[8 * j + 7]) + b[7]);
+        h[4 * j + 0] = *reinterpret_cast<__half2 *>(&o.x); h[4 * j + 1] = *reinterpret_cast<__half2 *>(&o.y);
+        h[4 * j + 2] = *reinterpret_cast<__half2 *>(&o.z); h[4 * j + 3] = *reinterpret_cast<__half2 *>(&o.w);
+        if (dbg) reinterpret_cast<uint4 *>(dbg)[j] = o;
+      }
+    };
+    for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
+      const int img = p.n_base + band / kBandsPerImg, p0 = (band % kBandsPerImg) * kBand2;
+      __half *dbg0 = p.conv_dbg ? p.conv_dbg + (size_t(img) * kConvW * kConvW + wo) * kC + hf * 32 : nullptr;
+      if (p0 == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) odd[k] = __floats2half2_rn(0.f, 0.f);
+      } else {
+        // the halo: odd row 2 p0 - 1 of pair 0 (its even row belongs to the band above)
+        const uint32_t acc = seq % kPairDepth;
+        ptx::mbar_wait(tfull + acc, (seq / kPairDepth) & 1);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(taddr0 + acc * 128 + 64, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty + acc);
+        ++seq;
+        to_half(v, odd, dbg0 ? dbg0 + size_t(2 * p0 - 1) * kConvW * kC : nullptr);
+      }
+      for (int pr = p0; pr < p0 + kBand2; ++pr, ++seq) {
+        const uint32_t acc = seq % kPairDepth;
+        ptx::mbar_wait(tfull + acc, (seq / kPairDepth) & 1);
+        ptx::tc_fence_after();
+        uint32_t va[32], vb[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(taddr0 + acc * 128, va);
+        ptx::tmem_ld_32x32(taddr0 + acc * 128 + 64, vb);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty + acc);
+        __half2 ev[16], cur[16];
+        to_half(va, ev, dbg0 ? dbg0 + size_t(2 * pr) * kConvW * kC : nullptr);
+        to_half(vb, cur, dbg0 ? dbg0 + size_t(2 * pr + 1) * kConvW * kC : nullptr);
+        const uint32_t slot = hist_a + (pooled & 1) * kHistBytes + uint32_t(wo) * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) oh[k] = __hmax2(__hmax2(odd[4 * j + k], ev[4 * j + k]), cur[4 * j + k]);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t((4 * hf + j) ^ (wo & 7)) << 4)),
+                       "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                       : "memory");
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) odd[k] = cur[k];
+        ptx::named_bar_sync(1, 256);
+        const uint32_t vrow = hist_a + (pooled & 1) * kHistBytes;
+        ++pooled;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int pw = pw0 + 32 * i;
+          __half2 m[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = __floats2half2_rn(0.f, 0.f);
+          bool first = pw > 0;
+#pragma unroll
+          for (int dc = -1; dc <= 1; ++dc) {
+            const int col = 2 * pw + dc;
+            if (col < 0) continue;
+            const uint4 x = ptx::lds_v4u(vrow + uint32_t(col) * 128u + (uint32_t(chunk ^ (col & 7)) << 4));
+            const __half2 *xh = reinterpret_cast<const __half2 *>(&x);
+            if (first) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) m[k] = xh[k];
+              first = false;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], xh[k]);
+            }
+          }
+          const size_t o = ((size_t(img) * kPoolW + pr) * kPoolW + pw) * kC + chunk * 8;
+          uint4 ro;
+          __half2 *rh = reinterpret_cast<__half2 *>(&ro);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rh[k] = m[k];
+          if (p.raw) *reinterpret_cast<uint4 *>(p.raw + o) = ro;
+          uint4 po;
+          uint32_t *pw32 = reinterpret_cast<uint32_t *>(&po);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 y = __half22float2(m[k]);
+            pw32[k] = pack2_relu(fmaf(y.x, ps[2 * k], pf[2 * k]), fmaf(y.y, ps[2 * k + 1], pf[2 * k + 1]));
+          }
+          *reinterpret_cast<uint4 *>(p.pre + o) = po;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kPairDepth * 128);
+  }
+  ptx::stamp_end(p.tstamp);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
+
+size_t root2_packed_weight_elems() { return kW2Bytes / 2; }
+
+void root2_pack_weights(const float *w_hwio, __half *dst) {
+  // HWIO [7][7][3][64] -> 18 x [k-chunk 2][row-group 16][8 rows][8 k] fp16 (un-swizzled K-major operand of 128 rows):
+  // MMA t = 2 * kpos + jp; rows 0..63 = conv row a (kernel row kpos), rows 64..127 = conv row a + 1 (kernel row kpos - 2)
+  for (size_t i = 0; i < size_t(kW2Bytes / 2); ++i) dst[i] = __float2half_rn(0.f);
+  for (int t = 0; t < kPairMmas; ++t) {
+    const int kpos = t >> 1, jp = t & 1;
+    for (int k = 0; k < 16; ++k) {
+      const int kw = 2 * (2 * jp + (k >> 3)) + ((k >> 2) & 1), ch = k & 3;
+      if (kw > 6 || ch > 2) continue;
+      for (int row = 0; row < 128; ++row) {
+        const int kh = row < 64 ? kpos : kpos - 2, o = row & 63;
+        if (kh < 0 || kh > 6) continue;
+        dst[size_t(t) * 2048 + (k >> 3) * 1024 + (row >> 3) * 64 + (row & 7) * 8 + (k & 7)] =
+            __float2half_rn(w_hwio[((size_t(kh) * 7 + kw) * 3 + ch) * kC + o]);
+      }
+    }
+  }
+}
+
+metro_status root_fused2_launch(const void *images, bool u8, const __half *wpack2, const float *bias, const float *pscale,
+                                const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base, int num_sms,
+                                cudaStream_t stream, unsigned long long *tstamp) {
+  if (n == 0) return METRO_OK;
+  static PerDeviceOnce configured;     // function attributes are per device
+  metro_status cst = configured.run([] {
+    METRO_CUDA(cudaFuncSetAttribute(root_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    return METRO_OK;
+  });
+  if (cst != METRO_OK) return cst;
+  Root2Params p{};
+  p.images = images; p.u8 = u8 ? 1 : 0; p.wpack = wpack2; p.bias = bias; p.pscale = pscale; p.pshift = pshift;
+  p.raw = raw; p.pre = pre; p.conv_dbg = conv_dbg; p.n = n; p.n_base = n_base; p.prof = nullptr; p.tstamp = tstamp;
+  const int n_bands = n * (kPoolW / kBand2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(n_bands < num_sms ? n_bands : num_sms)); cfg.blockDim = dim3(kThreads2);
+  cfg.dynamicSmemBytes = k2SmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("METRO_NO_PDL") != nullptr;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  METRO_CUDA(cudaLaunchKernelEx(&cfg, root_fused2_kernel, p));
+  return METRO_OK;
+}
 
 size_t root_packed_image_elems() { return size_t(kSide) * kPairs * 8; }
 size_t root_packed_weight_elems() { return kWBytes / 2; }

@@ -18,5 +18,12 @@ metro_status root_fused_launch(const void *image_map, const __half *wpack, const
                                const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base,
                                int num_sms, cudaStream_t stream, long long *prof = nullptr,
                                unsigned int *sig_flags = nullptr);
+// ---- version 2: the image pack folded into the kernel (loader warps convert the caller's float32 / uint8 rows into a
+// shared-memory ring), two conv rows per N = 128 accumulator.  `images` points at crop 0 of this call's input. ----
+size_t root2_packed_weight_elems();
+void root2_pack_weights(const float *w_hwio, __half *dst);
+metro_status root_fused2_launch(const void *images, bool u8, const __half *wpack2, const float *bias, const float *pscale,
+                                const float *pshift, __half *raw, __half *pre, __half *conv_dbg, int n, int n_base, int num_sms,
+                                cudaStream_t stream, unsigned long long *tstamp = nullptr);
 constexpr unsigned int kRootBandsPerCrop = 8;   // what a crop's counter reaches when sig_flags is given
 }  // namespace metro
