@@ -443,27 +443,55 @@ __global__ void __launch_bounds__(kThreads2, 1) root_fused2_kernel(const __grid_
         const bool first = j == (p0 == 0 ? 1 : 0);
         const int r_lo = first ? 2 * a - 3 : 2 * a + 2, r_hi = 2 * a + 5;     // input rows this pair adds to the ring
         // rows overwritten now were last read by the pair 4 back (kRingRows = 32 makes that hold at a band start too)
-        if (seq >= kPairDepth) ptx::mbar_wait(rempty + seq % kPairDepth, ((seq / kPairDepth) & 1) ^ 1);
-        for (int r0 = r_lo; r0 <= r_hi; r0 += 2) {
-          const int r = r0 + half;
-          if (r <= r_hi) {
+        bool slot_free = seq < kPairDepth;         // waited for just before the first store: the loads do not need the slot
+        // L2 prefetch of the rows two pairs ahead (the crops come from HBM: this turns the DRAM latency of the loads
+        // below into an L2 hit by the time they are issued); one 128-byte line per thread
+        {
+          const int pr_lo = r_hi + 5, pr_rows = 4;                      // rows 2(a+4)+2 .. +5 of pair j + 2
+          const int line = lt;                                          // 0..127
+          const int bytes_per_row = kSide * 3 * (p.u8 ? 1 : 4);
+          const int off = line * 128;
+          if (off < pr_rows * bytes_per_row && pr_lo >= 0 && pr_lo + pr_rows <= kSide && j + 2 <= kBand2)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + size_t(pr_lo) * bytes_per_row + off));
+        }
+        // all loads of up to three rounds (two rows each) are issued before the first conversion: the loader is bound by
+        // global-load latency, not by bytes
+        for (int rb = r_lo; rb <= r_hi; rb += 6) {
+          float4 f[3][3];
+          uint32_t w[3][3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int r = rb + 2 * k + half;
+            if (r <= r_hi && r >= 0 && r < kSide) {
+              if (p.u8) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(src + (size_t(r) * kSide + 4 * t) * 3);
+                w[k][0] = q[0]; w[k][1] = q[1]; w[k][2] = q[2];
+              } else {
+                const float4 *q = reinterpret_cast<const float4 *>(src + (size_t(r) * kSide + 4 * t) * 12);
+                f[k][0] = q[0]; f[k][1] = q[1]; f[k][2] = q[2];
+              }
+            }
+          }
+          if (!slot_free) { ptx::mbar_wait(rempty + seq % kPairDepth, ((seq / kPairDepth) & 1) ^ 1); slot_free = true; }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int r = rb + 2 * k + half;
+            if (r > r_hi) continue;
             uint2 o[4];
             if (r < 0 || r >= kSide) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) o[k] = make_uint2(0u, 0u);
+              for (int i = 0; i < 4; ++i) o[i] = make_uint2(0u, 0u);
             } else if (p.u8) {
-              const uint32_t *q = reinterpret_cast<const uint32_t *>(src + (size_t(r) * kSide + 4 * t) * 3);
-              const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+              const uint32_t w0 = w[k][0], w1 = w[k][1], w2 = w[k][2];
               const unsigned char b[12] = {(unsigned char)w0, (unsigned char)(w0 >> 8), (unsigned char)(w0 >> 16), (unsigned char)(w0 >> 24),
                                            (unsigned char)w1, (unsigned char)(w1 >> 8), (unsigned char)(w1 >> 16), (unsigned char)(w1 >> 24),
                                            (unsigned char)w2, (unsigned char)(w2 >> 8), (unsigned char)(w2 >> 16), (unsigned char)(w2 >> 24)};
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                o[k] = make_uint2(pack2(float(b[3 * k]) * (1.0f / 255.0f), float(b[3 * k + 1]) * (1.0f / 255.0f)),
-                                  pack2(float(b[3 * k + 2]) * (1.0f / 255.0f), 0.f));
+              for (int i = 0; i < 4; ++i)
+                o[i] = make_uint2(pack2(float(b[3 * i]) * (1.0f / 255.0f), float(b[3 * i + 1]) * (1.0f / 255.0f)),
+                                  pack2(float(b[3 * i + 2]) * (1.0f / 255.0f), 0.f));
             } else {
-              const float4 *q = reinterpret_cast<const float4 *>(src + (size_t(r) * kSide + 4 * t) * 12);
-              const float4 f0 = q[0], f1 = q[1], f2 = q[2];
+              const float4 f0 = f[k][0], f1 = f[k][1], f2 = f[k][2];
               o[0] = make_uint2(pack2(f0.x, f0.y), pack2(f0.z, 0.f));
               o[1] = make_uint2(pack2(f0.w, f1.x), pack2(f1.y, 0.f));
               o[2] = make_uint2(pack2(f1.z, f1.w), pack2(f2.x, 0.f));
@@ -473,8 +501,8 @@ __global__ void __launch_bounds__(kThreads2, 1) root_fused2_kernel(const __grid_
             const uint32_t slot = (ring + uint32_t(r - r_lo)) % kRingRows;
             const uint32_t dst = ptx::smem_u32(smem) + slot * kRowBytes + 32u * t + 24u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + 8u * k), "r"(o[k].x), "r"(o[k].y) : "memory");
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst + 8u * i), "r"(o[i].x), "r"(o[i].y) : "memory");
           }
         }
         ring = (ring + uint32_t(r_hi - r_lo + 1)) % kRingRows;
