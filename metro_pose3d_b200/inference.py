@@ -33,7 +33,8 @@ class MetroModel:
     def __init__(self, arch: str = 'resnet_v2_50', stride: int = 16, dataset: str = 'h36m',
                  weights=None, max_batch: int = 256, device: int = 0, head_dtype: str = 'f32',
                  keep_activations: bool = False, seed: int = 0, n_joints_model: Optional[int] = None,
-                 permutation: Optional[Sequence[int]] = None, precision: str = 'f16', joint_info=None):
+                 permutation: Optional[Sequence[int]] = None, precision: str = 'f16', joint_info=None,
+                 centered_stride: bool = True):
         """``precision``: 'f16' = the tensor-core path (the reference's default float16 export, src/options.py:73);
         'strict' = float64 on CUDA cores (tighter than the reference's ``--dtype float32`` export; slow, for
         verification); 'strict_f16' = float64 arithmetic with the float16 graph's storage roundings."""
@@ -44,14 +45,14 @@ class MetroModel:
         self.permutation = list(permutation) if permutation is not None else export_permutation(dataset)
         if joint_info is None and permutation is None:
             joint_info = exported_joint_info(dataset)
-        self.spec = NetSpec(arch, stride, self.n_joints_model)      # raises ValueError like the reference
+        self.spec = NetSpec(arch, stride, self.n_joints_model, centered_stride=centered_stride)   # raises ValueError like the reference
         self.device = device
         self.max_batch = max_batch
         self.precision = precision
         self.head_dtype = {'f32': _lib.METRO_F32, 'f16': _lib.METRO_F16}[head_dtype]
         self._cspec = _lib.make_spec(arch, stride, self.n_joints_model, self.permutation, max_batch,
                                      head_dtype=self.head_dtype, keep_activations=keep_activations,
-                                     precision=_lib.PRECISIONS[precision],
+                                     precision=_lib.PRECISIONS[precision], centered_stride=centered_stride,
                                      joint_names=None if joint_info is None else list(joint_info.names),
                                      joint_edges=None if joint_info is None else list(joint_info.edges))
         if weights is None:
@@ -78,7 +79,7 @@ class MetroModel:
         ji = JointInfo(list(fm.joint_names), [tuple(int(v) for v in e) for e in fm.joint_edges])
         model = cls(fm.arch, fm.stride, dataset='h36m', weights=fm.weights, max_batch=max_batch, device=device,
                     head_dtype=head_dtype, keep_activations=keep_activations, n_joints_model=fm.n_joints_model,
-                    permutation=fm.permutation, precision=precision, joint_info=ji)
+                    permutation=fm.permutation, precision=precision, joint_info=ji, centered_stride=fm.centered_stride)
         model.dataset = 'frozen-graph'
         return model
 

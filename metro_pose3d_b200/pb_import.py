@@ -184,7 +184,7 @@ def parse_graph_def(data: bytes) -> 'OrderedDict[str, Node]':
                         key = bytes(v3).decode()
                     elif n3 == 2:
                         value = v3
-                if key in ('value', 'strides', 'dilations', 'data_format') and value is not None:
+                if key in ('value', 'strides', 'dilations', 'data_format', 'padding') and value is not None:
                     node.attr[key] = _parse_attr(value)
         nodes[node.name] = node
     return nodes
@@ -209,6 +209,22 @@ def _const_of(nodes: Dict[str, Node], ref: str) -> Optional[np.ndarray]:
     return None
 
 
+def _const_name_of(nodes: Dict[str, Node], ref: str) -> Optional[str]:
+    """Name of the Const node an input reference resolves to (through Identity / Cast ...)."""
+    for _ in range(16):
+        name = ref.lstrip('^').split(':')[0]
+        node = nodes.get(name)
+        if node is None:
+            return None
+        if node.op == 'Const':
+            return name
+        if node.op in _PASS_THROUGH and node.inputs:
+            ref = node.inputs[0]
+            continue
+        return None
+    return None
+
+
 class FrozenModel:
     """What a frozen MeTRo graph contains, in this repository's terms."""
 
@@ -217,6 +233,7 @@ class FrozenModel:
         self.stride = 0
         self.n_joints_model = 0
         self.depth = 8
+        self.centered_stride = True
         self.permutation: List[int] = []
         self.joint_names: List[str] = []
         self.joint_edges = np.zeros((0, 2), np.int64)
@@ -224,7 +241,7 @@ class FrozenModel:
 
     @property
     def spec(self) -> NetSpec:
-        return NetSpec(self.arch, self.stride, self.n_joints_model)
+        return NetSpec(self.arch, self.stride, self.n_joints_model, centered_stride=self.centered_stride)
 
 
 def import_frozen_graph(data: bytes, depth: int = 8) -> FrozenModel:
@@ -234,6 +251,7 @@ def import_frozen_graph(data: bytes, depth: int = 8) -> FrozenModel:
     found: Dict[str, np.ndarray] = {}
     decomposed: Dict[str, Dict[str, np.ndarray]] = {}     # BN scope -> {'scale', 'offset'} of a non-fused batch norm
     stride_product = 1
+    strided_padding: Dict[str, str] = {}                  # scope of every stride-2 3x3 convolution -> its padding attribute
     for node in nodes.values():
         if '/resnet_v2_' not in node.name:
             continue
@@ -248,9 +266,17 @@ def import_frozen_graph(data: bytes, depth: int = 8) -> FrozenModel:
             w = _const_of(nodes, node.inputs[1])
             if w is None:
                 raise ValueError(f'{node.name}: filter is not a constant')
+            # graph transforms may rename the convolution (fold_batch_norms gives it the name of the multiplication it
+            # absorbed): when the filter constant still carries the variable's name, that name decides the scope
+            wname = _const_name_of(nodes, node.inputs[1]) or ''
+            if wname.endswith('/weights') and '/resnet_v2_' in wname:
+                scope = wname.split('/resnet_v2_', 1)[1].partition('/')[2].rsplit('/', 1)[0]
             found[f'{scope}/weights'] = np.asarray(w, np.float32)
             s = node.attr.get('strides') or [1]
             stride_product *= max(s)
+            pad = node.attr.get('padding')
+            if max(s) == 2 and np.asarray(w).shape[0] == 3 and isinstance(pad, (bytes, bytearray)):
+                strided_padding[scope] = bytes(pad).decode()
         elif node.op == 'BiasAdd':
             b = _const_of(nodes, node.inputs[1])
             if b is None:
@@ -297,6 +323,20 @@ def import_frozen_graph(data: bytes, depth: int = 8) -> FrozenModel:
     m.n_joints_model = head // depth
     m.stride = stride_product
     spec = m.spec                                        # raises ValueError like the reference for a bad stride
+    # FLAGS.centered_stride (src/options.py:118) is not stored in the graph, but it shows: conv2d_same emits a SAME
+    # convolution for the strided unit of the centred block and an explicit pad + VALID convolution for every other
+    # strided unit (resnet_utils.py:120-135, resnet_v2.py:277-302).  A --no-centered-stride export has VALID everywhere.
+    if strided_padding:
+        def pattern(sp):
+            return {f'{u.name}/bottleneck_v2/conv2': ('SAME' if u.shift else 'VALID') for u in sp.units if u.stride == 2}
+        if strided_padding == pattern(spec):
+            pass
+        elif strided_padding == pattern(NetSpec(m.arch, m.stride, m.n_joints_model, centered_stride=False)):
+            m.centered_stride = False
+            spec = m.spec
+        else:
+            raise ValueError(f'the padding of the strided convolutions ({strided_padding}) matches neither a centred-stride nor a '
+                             'plain export of this architecture / stride')
     for name, shape in blob_order(spec):
         if name not in found:
             raise ValueError(f'the graph has no constant for {name}')

@@ -68,7 +68,7 @@ def node(name, op, inputs=(), **attrs) -> bytes:
 
 
 def frozen_graph(spec, weights, permutation, joint_names, joint_edges, half=False, prefix='MainPart', bn_form='fused',
-                 eps=1e-5):
+                 eps=1e-5, fold_renames=False):
     """GraphDef bytes.  Constants get fold_constants-style names (not the variable names) and reach their
     consumers through Identity nodes; fp16 graphs store half constants, alternating the two TensorProto
     encodings (tensor_content / typed value list).
@@ -82,9 +82,9 @@ def frozen_graph(spec, weights, permutation, joint_names, joint_edges, half=Fals
     root = f'{prefix}/{spec.arch}'
     counter = [0]
 
-    def const(value):
+    def const(value, name=None):
         counter[0] += 1
-        name = f'{root}/_cf_{counter[0]}'
+        name = name or f'{root}/_cf_{counter[0]}'
         v = np.asarray(value, np.float16 if half else np.float32)
         form = 'content' if (counter[0] % 2 or v.size > 4096) else 'list'
         out.append(node(name, 'Const', value=attr_tensor(v, form)))
@@ -104,9 +104,15 @@ def frozen_graph(spec, weights, permutation, joint_names, joint_edges, half=Fals
         if fold:
             sc, off = scale_offset(f'{scope}/BatchNorm')
             w = np.asarray(w, np.float64) * sc                       # HWIO: the scale runs along the output channels
-        out.append(node(f'{root}/{scope}/Conv2D', 'Conv2D', [src, const(w)],
-                        strides=attr_ints([1, 1, s, s]), data_format=attr_str('NCHW')))
-        last = f'{root}/{scope}/Conv2D'
+        # conv2d_same (resnet_utils.py:120-135): SAME for stride 1 and for centred strides, explicit pad + VALID otherwise
+        same = c.stride == 1 or (c.k > 1 and c.pad_lo + c.pad_hi < c.k + (c.k - 1) * (c.rate - 1) - 1) or c.k == 1
+        # fold_renames: the rewritten convolution carries the name of the multiplication it absorbed, while its filter
+        # constant keeps the variable's name -- the naming a graph-transform tool may leave behind
+        cname = f'{root}/{scope}/BatchNorm/batchnorm/mul_1' if (fold and fold_renames) else f'{root}/{scope}/Conv2D'
+        out.append(node(cname, 'Conv2D', [src, const(w, f'{root}/{scope}/weights' if fold_renames else None)],
+                        strides=attr_ints([1, 1, s, s]), data_format=attr_str('NCHW'),
+                        padding=attr_str('SAME' if same else 'VALID')))
+        last = cname
         if c.has_bias:
             out.append(node(f'{root}/{scope}/BiasAdd', 'BiasAdd', [last, const(weights[f'{scope}/biases'])]))
             last = f'{root}/{scope}/BiasAdd'

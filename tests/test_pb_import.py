@@ -95,3 +95,32 @@ def test_folded_batch_norms_give_the_same_network(arch, stride):
         a = OracleNet(spec, w, perm, 'fp64')(img)
         b = OracleNet(spec, dict(m.weights), perm, 'fp64')(img)
         assert np.abs(a - b).max() < 2e-3, np.abs(a - b).max()       # float32 rounding of the folded constants (measured 2e-4 mm)
+
+
+def test_centered_stride_is_read_off_the_padding_attributes():
+    """FLAGS.centered_stride is not stored in the graph; conv2d_same's SAME / explicit-pad + VALID choice per strided unit
+    (resnet_utils.py:120-135) gives it away.  A --no-centered-stride export must not be loaded as a centred model."""
+    ji = exported_joint_info('h36m')
+    for centred in (True, False):
+        for stride in (32, 16, 8):
+            spec = NetSpec('resnet_v2_50', stride, 17, centered_stride=centred)
+            w = synth_weights(spec, 1)
+            m = import_frozen_graph(frozen_graph(spec, w, export_permutation('h36m'), list(ji.names), np.asarray(ji.edges)))
+            assert m.centered_stride is centred and m.stride == stride
+            assert [u.shift for u in m.spec.units] == [u.shift for u in spec.units]
+
+
+def test_folded_convolution_renamed_by_the_transform_tool():
+    """A folded convolution that took the name of the multiplication it absorbed is found through its filter constant,
+    which keeps the variable's name."""
+    spec = NetSpec('resnet_v2_50', 32, 17)
+    w = synth_weights(spec, 2)
+    ji = exported_joint_info('h36m')
+    data = frozen_graph(spec, w, export_permutation('h36m'), list(ji.names), np.asarray(ji.edges), bn_form='folded',
+                        fold_renames=True)
+    m = import_frozen_graph(data)
+    plain = import_frozen_graph(frozen_graph(spec, w, export_permutation('h36m'), list(ji.names), np.asarray(ji.edges),
+                                             bn_form='folded'))
+    assert list(m.weights) == list(plain.weights)
+    for k in m.weights:
+        assert np.array_equal(m.weights[k], plain.weights[k]), k
