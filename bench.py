@@ -146,6 +146,24 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def agree_on_time_and_steps(ms_local, steps, world, dist=None, device=None):
+    """Max over ranks of the per-step time and ONE step count for the clock-sampling extension of the timed loop
+    (>= 1 s of steps).  Every step is a collective, so the count must be identical on every rank: it is derived from the
+    all-reduced time and then broadcast from rank 0 (a rank-local count hung an 8-GPU run of this bench in round 2)."""
+    import torch
+    ms = ms_local
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ext = max(steps, min(2000, int(1.0 / max(ms * 1e-3, 1e-4))))
+    if world > 1:
+        t = torch.tensor([ext], device=device, dtype=torch.int64)
+        dist.broadcast(t, 0)
+        ext = int(t.item())
+    return ms, ext
+
+
 def make_config(cfg_name, arch, stride, j, per_gpu, world):
     """The workload description both arms print (the driver compares them)."""
     return {'workload': f'config {cfg_name}: {arch} stride_{stride} {j} joints, batch {per_gpu}/GPU',
@@ -273,9 +291,11 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1) / args.steps
+    ms_local = ms                                   # this rank's device time per step
     # the timed region above is exactly `steps` steps (~0.1 s: a handful of NVML samples); the same loop is repeated
     # for >= 1 s purely to sample clocks / throttle reasons under sustained load -- its time is reported as an extra
-    ext_steps = max(args.steps, int(1.0 / max(ms * 1e-3, 1e-4)))
+    ms, ext_steps = agree_on_time_and_steps(ms_local, args.steps, world, dist, dev)
+    value = n * world / (ms * 1e-3)
     sampler2 = ClockSampler(local_rank)
     if rank == 0:
         sampler2.start()
@@ -290,12 +310,6 @@ def main():
     ms_ext = ev2.elapsed_time(ev3) / ext_steps
     if world > 1:
         dist.barrier()
-    ms_local = ms                                   # this rank's device time per step
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = n * world / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call: pinned host float32 in, host poses out ----
     host_in = torch.rand((n, 256, 256, 3), dtype=torch.float32).pin_memory()

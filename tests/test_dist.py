@@ -68,3 +68,37 @@ def test_two_rank_gather_equals_single_process(n):
         assert p.exitcode == 0
     ref = decode_ref(synth_head(n, 8, 17, seed=3), 17, 32, export_permutation('h36m')).astype(np.float32)
     assert np.array_equal(got, ref)
+
+
+def _count_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_module', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    # ranks measure different step times (4.3 ms vs 4.9 ms): a rank-local count would be 232 vs 204 steps
+    ms, ext = bench.agree_on_time_and_steps(4.3 if rank == 0 else 4.9, 20, world, dist, torch.device('cpu'))
+    q.put((rank, ms, ext))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_ranks_agree_on_the_extension_step_count():
+    """Every bench step ends in a collective: all ranks must loop the same number of times (regression test for the
+    round-2 hang of the 8-GPU run, where each rank derived the count from its own timing)."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_count_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] == 4.9 and got[0][2] == got[1][2] == 204
