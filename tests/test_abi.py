@@ -76,3 +76,48 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b|#include\s+".*oracle', text, flags=re.M), \
                     f'{f} pulls in the oracle'
+
+
+def test_argument_errors_of_the_side_entry_points_need_no_gpu(libmetro):
+    """The validation of the round-2 entry points happens before any CUDA call: bad arguments come back as
+    METRO_ERR_VALUE (the reference's ValueError) on a machine without a GPU too."""
+    vp = C.c_void_p
+    one = vp(16)                                          # a non-null pointer that is never dereferenced on these paths
+    assert libmetro.metro_back_project(one, one, one, -1, 17, 16, 1, 256, C.c_float(2200.0), one, None) == lib.METRO_ERR_VALUE
+    assert libmetro.metro_back_project(one, one, one, 2, 0, 16, 1, 256, C.c_float(2200.0), one, None) == lib.METRO_ERR_VALUE
+    assert libmetro.metro_back_project(None, one, one, 2, 17, 16, 1, 256, C.c_float(2200.0), one, None) == lib.METRO_ERR_VALUE
+    assert libmetro.metro_back_project(one, one, one, 0, 17, 16, 1, 256, C.c_float(2200.0), one, None) == lib.METRO_OK   # empty batch
+    src = (lib.CropSrc * 1)()
+    src[0].frame_dev, src[0].height, src[0].width, src[0].row_stride_bytes = 16, 480, 640, 100       # stride < 3 * width
+    assert libmetro.metro_extract_crops(src, 1, 256, 0, one, None) == lib.METRO_ERR_VALUE
+    assert b'source 0' in libmetro.metro_last_error()
+    src[0].row_stride_bytes = 1920
+    assert libmetro.metro_extract_crops(src, 1, 256, 300, one, None) == lib.METRO_ERR_VALUE             # border not a byte
+    assert libmetro.metro_extract_crops(src, 1, 0, 0, one, None) == lib.METRO_ERR_VALUE
+    src[0].height = 40000
+    assert libmetro.metro_extract_crops(src, 1, 256, 0, one, None) == lib.METRO_ERR_VALUE
+    assert b'32767' in libmetro.metro_last_error()
+    assert libmetro.metro_extract_crops(src, 0, 256, 0, one, None) == lib.METRO_OK
+    perm = (C.c_int32 * 17)(*range(17))
+    d = lib.SoftargmaxDesc(0, 17, 8, 16, 1, 256, 2200.0, 17, C.cast(perm, C.POINTER(C.c_int32)), 0, 0, 0, 0)
+    assert libmetro.metro_heatmap_z(C.byref(d), one, 2, one, None) == lib.METRO_ERR_VALUE
+    d.side = 16
+    assert libmetro.metro_heatmap_z(C.byref(d), None, 2, one, None) == lib.METRO_ERR_VALUE
+    assert libmetro.metro_softargmax_coords(C.byref(d), one, 2, None, None, one, None) == lib.METRO_ERR_VALUE     # no output at all
+    assert libmetro.metro_get_joint_info(None, None, 0, None, None, 0, None, None) == lib.METRO_ERR_VALUE
+    assert libmetro.metro_graph_stats(None, None, None) == lib.METRO_ERR_VALUE
+
+
+def test_spec_validation_of_precision_and_joint_tables(libmetro):
+    """metro_create checks the new spec fields before it looks for a device."""
+    blob = np.zeros(4, np.float32)
+    h = C.c_void_p()
+    spec = lib.make_spec('resnet_v2_50', 32, 17, list(range(17)), precision=7)
+    assert libmetro.metro_create(C.byref(spec), blob.ctypes.data_as(C.c_void_p), blob.size, 0, C.byref(h)) == lib.METRO_ERR_VALUE
+    assert b'precision' in libmetro.metro_last_error()
+    spec = lib.make_spec('resnet_v2_50', 32, 17, list(range(17)), joint_names=['a', 'b'])            # 2 names for 17 joints
+    assert libmetro.metro_create(C.byref(spec), blob.ctypes.data_as(C.c_void_p), blob.size, 0, C.byref(h)) == lib.METRO_ERR_VALUE
+    assert b'joint_names' in libmetro.metro_last_error()
+    spec = lib.make_spec('resnet_v2_50', 32, 17, list(range(17)), joint_edges=[(0, 99)])
+    assert libmetro.metro_create(C.byref(spec), blob.ctypes.data_as(C.c_void_p), blob.size, 0, C.byref(h)) == lib.METRO_ERR_VALUE
+    assert b'joint_edges' in libmetro.metro_last_error()

@@ -51,3 +51,39 @@ def test_constant_shift_per_joint_and_root_is_zero(side, seed, shift):
     b = decode_ref(y.reshape(2, side, side, 136), 17, 256 // side, _PERM)
     assert np.abs(a - b).max() < 1e-6
     assert np.all(a[:, _PERM.index(16)] == 0)            # the pelvis (last model joint) is the origin
+
+
+# ---- crop extraction oracle (oracle/crop_oracle.py: reproject_image_fast = homography + cv2.remap arithmetic) ----
+from oracle.crop_oracle import reproject_image_fast_ref, remap_bilinear_u8
+
+
+@settings(max_examples=25, deadline=None)
+@given(h=st.integers(8, 40), w=st.integers(8, 40), dx=st.integers(-6, 6), dy=st.integers(-6, 6), seed=st.integers(0, 10_000))
+def test_integer_translation_is_an_exact_shift_with_constant_border(h, w, dx, dy, seed):
+    """A homography that translates by whole pixels copies pixels (the single non-zero weight is 32767 / 32768 of OpenCV's
+    int16 table, which still rounds to the pixel) and fills what falls outside the frame with the border value."""
+    frame = np.random.RandomState(seed).randint(0, 256, (h, w, 3)).astype(np.uint8)
+    hm = np.array([[1, 0, dx], [0, 1, dy], [0, 0, 1]], np.float32)
+    got = reproject_image_fast_ref(frame, hm, h, w, border_value=9)
+    yy, xx = np.mgrid[:h, :w]
+    sy, sx = yy + dy, xx + dx
+    inside = (sy >= 0) & (sy < h) & (sx >= 0) & (sx < w)
+    want = np.where(inside[..., None], frame[np.clip(sy, 0, h - 1), np.clip(sx, 0, w - 1)], 9).astype(np.uint8)
+    assert np.array_equal(got, want)
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 10_000), scale=st.floats(0.3, 3.0))
+def test_constant_image_stays_constant_inside_the_frame(seed, scale):
+    """Bilinear weights sum to 2^15 (or 2^15 - 1 on an exact pixel): a constant frame resamples to the same constant wherever
+    all four taps are inside, whatever the (here: scaling) homography."""
+    rng = np.random.RandomState(seed)
+    c = int(rng.randint(0, 256))
+    frame = np.full((32, 32, 3), c, np.uint8)
+    hm = np.array([[scale, 0, 3.3], [0, scale, 2.1], [0, 0, 1]], np.float32)
+    mx = (np.arange(8, dtype=np.float32) * np.float32(scale) + np.float32(3.3))[None, :].repeat(8, 0)
+    my = (np.arange(8, dtype=np.float32) * np.float32(scale) + np.float32(2.1))[:, None].repeat(8, 1)
+    got = reproject_image_fast_ref(frame, hm, 8, 8)
+    inside = (mx >= 0) & (mx <= 30.9) & (my >= 0) & (my <= 30.9)
+    assert np.all(got[inside] == c)
+    assert np.array_equal(got, remap_bilinear_u8(frame, mx.astype(np.float32), my.astype(np.float32)))
