@@ -87,3 +87,29 @@ def test_constant_image_stays_constant_inside_the_frame(seed, scale):
     inside = (mx >= 0) & (mx <= 30.9) & (my >= 0) & (my <= 30.9)
     assert np.all(got[inside] == c)
     assert np.array_equal(got, remap_bilinear_u8(frame, mx.astype(np.float32), my.astype(np.float32)))
+
+
+# ---- absolute-scale variant (oracle true_root_depth_ref: volumetric.py:190-198,285) ----
+from oracle.metro_oracle import true_root_depth_ref
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 10_000), stride=st.sampled_from([4, 8, 16, 32]), j=st.sampled_from([17, 19, 53]))
+def test_back_projection_round_trip(seed, stride, j):
+    """Projecting the back-projected joints with the camera's intrinsics gives back the predicted image coordinates
+    (heatmap_to_image of the 2D part), the root joint sits at the given depth, and depths relative to the root are the
+    heatmap's z differences in millimetres -- for any camera, stride and joint count."""
+    rng = np.random.RandomState(seed)
+    n = 3
+    c = rng.rand(n, j, 3)
+    f = rng.uniform(200.0, 1500.0, n)
+    k = np.zeros((n, 3, 3))
+    k[:, 0, 0], k[:, 1, 1], k[:, 2, 2] = f, f * rng.uniform(0.9, 1.1, n), 1.0
+    k[:, 0, 2], k[:, 1, 2] = rng.uniform(100, 156, n), rng.uniform(100, 156, n)
+    z = rng.uniform(1500.0, 8000.0, n)
+    x = true_root_depth_ref(c, np.linalg.inv(k), z, stride)
+    proj = np.einsum('bij,bcj->bci', k, x / x[..., 2:3])
+    lrc = 255 - (255 % stride) - 1
+    assert np.abs(proj[..., :2] - (c[..., :2] * lrc + stride // 2)).max() < 1e-8
+    assert np.abs(x[:, -1, 2] - z).max() < 1e-9
+    assert np.abs((x[..., 2] - x[:, -1:, 2]) - (c[..., 2] - c[:, -1:, 2]) * 2200.0).max() < 1e-9
